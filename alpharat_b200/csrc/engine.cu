@@ -1,0 +1,721 @@
+// engine.cu — kernels and C-ABI of libalpharat_cuda.so (see include/alpharat_cuda.h).
+//
+// Compiled with -fmad=false: the tree kernels replay the reference's f32 arithmetic
+// operation-for-operation (search.rs, node.rs) and must not contract a*b+c into FMA.
+// The leaf-evaluator kernels live in nn_kernels.cu (separate translation unit, FMA allowed).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "mcts_device.cuh"
+
+namespace ar {
+
+// ---------------------------------------------------------------------------------------
+// Kernel parameters
+// ---------------------------------------------------------------------------------------
+struct RunParams {
+  // inputs (device)
+  const ar_game_pod* games;
+  const uint64_t* seeds;
+  int n_games;
+  // outputs (device)
+  ar_game_summary* summaries;
+  ar_position_record* positions;
+  int pos_stride;
+  ar_search_result* search_out;  // search-only mode
+  int search_only;
+  // search
+  SearchParams sp;
+  // per-slot storage
+  NodeRec* pools;
+  uint32_t pool_nodes;
+  uint32_t* path_bufs;
+  uint32_t path_stride;
+  uint16_t* remaps;
+  const uint16_t* coll_table;
+  uint32_t coll_table_len;
+  uint32_t max_depth;
+  uint32_t batch_cap;
+  int n_slots;
+  // bookkeeping
+  unsigned int* next_game;
+  unsigned long long* counters;  // [0] path_nodes [1] new_nodes
+  int* error_flag;
+  ar_progress* progress;  // mapped pinned host memory (may be null)
+};
+
+__host__ __device__ inline size_t warp_smem_bytes(uint32_t max_depth, uint32_t batch_cap) {
+  size_t b = (size_t)max_depth * sizeof(Level);      // level stack
+  b += (size_t)batch_cap * sizeof(GState);           // leaf states
+  b += 256;                                          // maze cost table (64 cells x 4)
+  b += (size_t)batch_cap * sizeof(TpEntry);          // batch entries
+  return (b + 15) & ~(size_t)15;
+}
+
+// One simulate_batch (search.rs:961-1073) with SmartUniformBackend fused in
+// (backend.rs:94-103: priors written when the node is created, values are 0).
+__device__ __forceinline__ void simulate_batch_uniform(WarpCtx& cx, const SearchParams& sp, Rng& rng,
+                                                       const GState& root_g, int root_turn,
+                                                       uint32_t bs, uint32_t& nn, uint32_t& term,
+                                                       uint32_t& coll, uint32_t coll_len, int lane) {
+  cx.epoch += 1;
+  cx.root_claimed = false;
+  uint32_t ci = cx.node_count < coll_len ? cx.node_count : coll_len - 1;
+  int collisions_left = (int)cx.coll_table[ci];
+  int n_tp = 0;
+  while ((uint32_t)n_tp < bs && collisions_left > 0 && cx.error == 0) {
+    uint32_t budget = min((uint32_t)collisions_left, bs - (uint32_t)n_tp);
+    uint32_t c = pick_nodes(cx, sp, rng, root_g, root_turn, budget, n_tp, true, lane);
+    collisions_left -= (int)c;
+    coll += c;
+  }
+  if (cx.error) return;
+  for (int e = 0; e < n_tp; ++e) {
+    uint8_t kind = cx.tp[e].kind;
+    if (kind == 1) term += 1; else nn += 1;
+    backup_entry(cx, e, 0.0f, 0.0f, nullptr, nullptr, lane);
+  }
+}
+
+__device__ __noinline__ void extract_and_store(WarpCtx& cx, const SearchParams& sp, int lane,
+                                               ar_search_result* out, uint32_t nn, uint32_t term,
+                                               uint32_t coll, float pol1[5], float pol2[5]) {
+  ar_search_result res;
+  extract_result(cx, sp, lane, res);
+  res.nn_evals = nn;
+  res.terminals = term;
+  res.collisions = coll;
+#pragma unroll
+  for (int a = 0; a < 5; ++a) { pol1[a] = res.policy_p1[a]; pol2[a] = res.policy_p2[a]; }
+  if (lane == 0) *out = res;
+}
+
+__device__ __forceinline__ void load_game(const ar_game_pod* pod, WarpCtx& cx, GState& g, int& turn,
+                                          int lane) {
+  cx.w = pod->width;
+  cx.cells = (int)pod->width * pod->height;
+  cx.max_turns = pod->max_turns;
+  turn = pod->turn;
+  __syncwarp();
+  for (int i = lane; i < 64; i += 32)  // 64 cells x 4 directions = 64 words
+    reinterpret_cast<uint32_t*>(cx.maze)[i] =
+        (i < cx.cells) ? reinterpret_cast<const uint32_t*>(pod->move_cost)[i] : 0u;
+  g.cheese = *reinterpret_cast<const uint64_t*>(pod->cheese);
+  g.p1 = (uint8_t)(pod->p1_y * pod->width + pod->p1_x);
+  g.p2 = (uint8_t)(pod->p2_y * pod->width + pod->p2_x);
+  g.mud1 = pod->p1_mud;
+  g.mud2 = pod->p2_mud;
+  g.s1x2 = (uint16_t)__float2int_rn(pod->p1_score * 2.0f);
+  g.s2x2 = (uint16_t)__float2int_rn(pod->p2_score * 2.0f);
+  __syncwarp();
+}
+
+// The uniform-prior self-play kernel: each warp claims games from an atomic counter
+// (game_worker_loop, selfplay.rs:609-650) and plays them to completion on device
+// (play_game, selfplay.rs:515-598).  search_only: one fresh-tree search per "game"
+// (rust_mcts_search, mcts/bindings.rs:228-304).
+__global__ void __launch_bounds__(128, 4) selfplay_uniform_kernel(RunParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int slot = blockIdx.x * 4 + wib;
+  if (slot >= p.n_slots) return;
+
+  uint8_t* base = smem + (size_t)wib * warp_smem_bytes(p.max_depth, p.batch_cap);
+  WarpCtx cx;
+  cx.levels = reinterpret_cast<Level*>(base);
+  cx.tp_state = reinterpret_cast<GState*>(base + (size_t)p.max_depth * sizeof(Level));
+  cx.maze = reinterpret_cast<uint8_t*>(cx.tp_state + p.batch_cap);
+  cx.tp = reinterpret_cast<TpEntry*>(cx.maze + 256);
+  cx.pool = p.pools + (size_t)slot * p.pool_nodes;
+  cx.path_buf = p.path_bufs + (size_t)slot * p.batch_cap * p.path_stride;
+  cx.remap = p.remaps + (size_t)slot * p.pool_nodes;
+  cx.coll_table = p.coll_table;
+  cx.pool_nodes = p.pool_nodes;
+  cx.path_stride = p.path_stride;
+  cx.max_depth = p.max_depth;
+  cx.epoch = 1;
+  cx.path_nodes = 0;
+  cx.new_nodes = 0;
+  cx.error = 0;
+  cx.node_count = 0;
+  cx.root_claimed = false;
+  const SearchParams sp = p.sp;
+
+  for (;;) {
+    unsigned int gi = 0;
+    if (lane == 0) gi = atomicAdd(p.next_game, 1u);
+    gi = __shfl_sync(FULL, gi, 0);
+    if (gi >= (unsigned)p.n_games) break;
+
+    GState g;
+    int turn;
+    load_game(p.games + gi, cx, g, turn, lane);
+    Rng rng = rng_seed(p.seeds[gi]);
+    const int cheese_available = __popcll(g.cheese);
+    cx.epoch += 1;
+    init_root(cx, g, lane);
+
+    uint32_t n_pos = 0;
+    unsigned long long tot_sims = 0, tot_nn = 0, tot_term = 0, tot_coll = 0;
+    ar_position_record* pos = p.positions ? p.positions + (size_t)gi * p.pos_stride : nullptr;
+
+    while (p.search_only || !game_over(g, turn, cx.max_turns)) {
+      // ---- run_search (search.rs:362-390)
+      uint32_t remaining = sp.n_sims, nn = 0, term = 0, coll = 0;
+      while (remaining > 0 && cx.error == 0) {
+        uint32_t bs = min(remaining, sp.batch_size);
+        uint32_t nn0 = nn, term0 = term;
+        simulate_batch_uniform(cx, sp, rng, g, turn, bs, nn, term, coll, p.coll_table_len, lane);
+        uint32_t produced = (nn - nn0) + (term - term0);
+        produced = produced > 1u ? produced : 1u;
+        remaining = remaining > produced ? remaining - produced : 0u;
+      }
+      if (cx.error) break;
+
+      float pol1[5], pol2[5];
+      ar_search_result* rout = p.search_only ? (p.search_out + gi) : &pos[n_pos].search;
+      extract_and_store(cx, sp, lane, rout, nn, term, coll, pol1, pol2);
+      if (p.search_only) break;
+
+      // ---- one self-play move (selfplay.rs:547-565)
+      uint32_t tv = 0;
+      if (lane == 0) tv = rout->total_visits;
+      tv = __shfl_sync(FULL, tv, 0);
+      tot_sims += tv; tot_nn += nn; tot_term += term; tot_coll += coll;
+      int a1 = rng_sample_action(rng, pol1);
+      int a2 = rng_sample_action(rng, pol2);
+      if (lane == 0) {
+        ar_position_record& pr = pos[n_pos];
+        pr.p1_x = (uint8_t)(g.p1 % cx.w); pr.p1_y = (uint8_t)(g.p1 / cx.w);
+        pr.p2_x = (uint8_t)(g.p2 % cx.w); pr.p2_y = (uint8_t)(g.p2 / cx.w);
+        pr.p1_mud = g.mud1; pr.p2_mud = g.mud2;
+        pr.action_p1 = (uint8_t)a1; pr.action_p2 = (uint8_t)a2;
+        pr.turn = (uint16_t)turn; pr.reserved = 0;
+        pr.p1_score = 0.5f * (float)g.s1x2; pr.p2_score = 0.5f * (float)g.s2x2;
+        uint64_t* cb = reinterpret_cast<uint64_t*>(pr.cheese);
+        cb[0] = g.cheese; cb[1] = 0; cb[2] = 0; cb[3] = 0;
+      }
+      n_pos += 1;
+
+      // advance_root maps raw actions through action_to_outcome_idx (tree.rs:283-295)
+      uint32_t rmeta = cx.pool[0].v[11].y;
+      int i = action_to_idx(meta_m1(rmeta), a1), j = action_to_idx(meta_m2(rmeta), a2);
+      uint32_t child = reinterpret_cast<const uint16_t*>(&cx.pool[0].v[12])[i * 5 + j];
+      game_step(g, a1, a2, cx.maze, cx.w);
+      turn += 1;
+      __syncwarp();
+      if (child != 0) {
+        compact_subtree(cx, child, lane);
+      } else {
+        cx.epoch += 1;
+        init_root(cx, g, lane);  // reinit, tree.rs:298-302
+      }
+    }
+
+    if (cx.error) break;
+    if (!p.search_only && lane == 0) {
+      ar_game_summary& s = p.summaries[gi];
+      s.game_index = gi;
+      s.n_positions = n_pos;
+      s.final_p1_score = 0.5f * (float)g.s1x2;
+      s.final_p2_score = 0.5f * (float)g.s2x2;
+      s.result = g.s1x2 > g.s2x2 ? 1 : (g.s2x2 > g.s1x2 ? 2 : 0);
+      s.cheese_available = (uint16_t)cheese_available;
+      s.total_simulations = tot_sims;
+      s.total_nn_evals = tot_nn;
+      s.total_terminals = tot_term;
+      s.total_collisions = tot_coll;
+      // final state, consumed by the host-side cheese-outcome attribution
+      s.reserved[0] = g.p1; s.reserved[1] = g.p2; s.reserved[2] = 0;
+      *reinterpret_cast<uint64_t*>(s.cheese_outcomes) = g.cheese;
+      if (p.progress) {
+        atomicAdd_system((unsigned long long*)&p.progress->positions_completed, (unsigned long long)n_pos);
+        atomicAdd_system((unsigned long long*)&p.progress->simulations_completed, tot_sims);
+        atomicAdd_system((unsigned long long*)&p.progress->nn_evals_completed, tot_nn);
+        atomicAdd_system((unsigned int*)&p.progress->games_completed, 1u);
+      }
+    }
+  }
+  if (lane == 0) {
+    atomicAdd(&p.counters[0], (unsigned long long)cx.path_nodes);
+    atomicAdd(&p.counters[1], (unsigned long long)cx.new_nodes);
+    if (cx.error) atomicCAS(p.error_flag, 0, (int)cx.error);
+  }
+}
+
+}  // namespace ar
+
+// =========================================================================================
+// Host side: engine object and C-ABI
+// =========================================================================================
+using namespace ar;
+
+struct ar_engine {
+  ar_engine_cfg cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  // per-slot storage
+  NodeRec* pools = nullptr;
+  uint32_t* path_bufs = nullptr;
+  uint16_t* remaps = nullptr;
+  uint16_t* coll_table = nullptr;
+  uint32_t pool_nodes = 0, path_stride = 0, max_depth = 0, batch_cap = 0, n_slots = 0;
+  ar_search_cfg coll_cfg{};
+  bool coll_valid = false;
+  // run buffers
+  ar_game_pod* d_games = nullptr;
+  uint64_t* d_seeds = nullptr;
+  ar_game_summary* d_summaries = nullptr;
+  ar_position_record* d_positions = nullptr;
+  ar_search_result* d_search = nullptr;
+  int cap_games = 0, cap_stride = 0, cap_search = 0;
+  int n_resident = 0, resident_stride = 0;
+  std::vector<ar_game_pod> h_games;  // kept for cheese-outcome attribution
+  unsigned int* d_next = nullptr;
+  unsigned long long* d_counters = nullptr;
+  int* d_error = nullptr;
+  ar_progress* h_progress = nullptr;  // mapped pinned
+  ar_progress* d_progress = nullptr;
+  uint64_t h2d = 0, d2h = 0, launches = 0;
+};
+
+static thread_local std::string g_create_error;
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      e->err = std::string(#call) + ": " + cudaGetErrorString(_e);                        \
+      return AR_ERR_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+static uint32_t host_collisions_left(uint32_t n, const ar_search_cfg& c) {  // search.rs:437-450
+  if (n >= c.collision_scaling_end) return c.collision_limit_max;
+  if (n <= c.collision_scaling_start) return c.collision_limit_min;
+  float ratio = (float)(n - c.collision_scaling_start) /
+                (float)(c.collision_scaling_end - c.collision_scaling_start);
+  float scaled = (float)c.collision_limit_min +
+                 ((float)c.collision_limit_max - (float)c.collision_limit_min) *
+                     powf(ratio, c.collision_scaling_power);
+  float r = roundf(scaled);
+  uint32_t v = !(r > 0.0f) ? 0u : (r >= 4294967296.0f ? 0xffffffffu : (uint32_t)r);
+  return std::min(std::max(v, c.collision_limit_min), c.collision_limit_max);
+}
+
+static ar_status ensure_coll_table(ar_engine* e, const ar_search_cfg& c) {
+  if (e->coll_valid && memcmp(&e->coll_cfg.collision_limit_min, &c.collision_limit_min,
+                              sizeof(uint32_t) * 4 + sizeof(float)) == 0)
+    return AR_OK;
+  std::vector<uint16_t> t(e->pool_nodes + 1);
+  for (uint32_t n = 0; n <= e->pool_nodes; ++n) {
+    uint32_t v = host_collisions_left(n, c);
+    t[n] = (uint16_t)std::min<uint32_t>(v, 65535u);
+  }
+  CK(cudaMemcpyAsync(e->coll_table, t.data(), t.size() * sizeof(uint16_t), cudaMemcpyHostToDevice,
+                     e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  e->coll_cfg = c;
+  e->coll_valid = true;
+  return AR_OK;
+}
+
+static ar_status validate_cfg(ar_engine* e, const ar_search_cfg* c) {
+  if (!c) { e->err = "search cfg is NULL"; return AR_ERR_INVALID_ARG; }
+  if (c->simulations == 0) { e->err = "simulations must be > 0"; return AR_ERR_INVALID_ARG; }
+  if (c->batch_size == 0 || c->batch_size > e->batch_cap) {
+    e->err = "batch_size " + std::to_string(c->batch_size) + " outside [1, engine max_batch_size=" +
+             std::to_string(e->batch_cap) + "]";
+    return AR_ERR_INVALID_ARG;
+  }
+  if (c->noise_epsilon > 0.0f) {
+    e->err = "noise_epsilon > 0 (Dirichlet root noise) is not implemented in this build";
+    return AR_ERR_UNSUPPORTED;
+  }
+  if (c->collision_limit_max > 65535u) { e->err = "collision_limit_max > 65535"; return AR_ERR_INVALID_ARG; }
+  return AR_OK;
+}
+
+static ar_status validate_games(ar_engine* e, const ar_game_pod* games, int n) {
+  if (n < 0 || (n > 0 && !games)) { e->err = "games is NULL"; return AR_ERR_INVALID_ARG; }
+  for (int i = 0; i < n; ++i) {
+    const ar_game_pod& g = games[i];
+    uint32_t cells = (uint32_t)g.width * g.height;
+    if (g.width == 0 || g.height == 0) { e->err = "game " + std::to_string(i) + ": empty board"; return AR_ERR_INVALID_ARG; }
+    if (cells > 64 || cells > e->cfg.max_cells) {
+      e->err = "game " + std::to_string(i) + ": " + std::to_string(g.width) + "x" + std::to_string(g.height) +
+               " board exceeds the 64-cell bitboard of this build";
+      return AR_ERR_UNSUPPORTED;
+    }
+    if (g.max_turns > e->cfg.max_turns) {
+      e->err = "game " + std::to_string(i) + ": max_turns " + std::to_string(g.max_turns) +
+               " exceeds engine max_turns " + std::to_string(e->cfg.max_turns);
+      return AR_ERR_INVALID_ARG;
+    }
+    if (g.p1_x >= g.width || g.p2_x >= g.width || g.p1_y >= g.height || g.p2_y >= g.height) {
+      e->err = "game " + std::to_string(i) + ": player outside the board";
+      return AR_ERR_INVALID_ARG;
+    }
+  }
+  return AR_OK;
+}
+
+extern "C" {
+
+uint32_t ar_abi_version(void) { return AR_ABI_VERSION; }
+
+const char* ar_last_error(const ar_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
+  if (!cfg || !out) { g_create_error = "cfg/out is NULL"; return AR_ERR_INVALID_ARG; }
+  if (cfg->abi_version != AR_ABI_VERSION) { g_create_error = "ABI version mismatch"; return AR_ERR_INVALID_ARG; }
+  ar_engine* e = new ar_engine();
+  e->cfg = *cfg;
+  auto fail = [&](ar_status s, const std::string& m) {
+    g_create_error = m;
+    ar_engine_destroy(e);
+    return s;
+  };
+  if (cfg->concurrent_games == 0) return fail(AR_ERR_INVALID_ARG, "concurrent_games must be > 0");
+  if (cfg->max_cells == 0 || cfg->max_cells > 64) return fail(AR_ERR_UNSUPPORTED, "max_cells must be in [1, 64] in this build");
+  if (cfg->max_batch_size == 0 || cfg->max_batch_size > MAX_BATCH) return fail(AR_ERR_INVALID_ARG, "max_batch_size must be in [1, 64]");
+  if (cfg->max_turns == 0 || cfg->max_turns > 120) return fail(AR_ERR_UNSUPPORTED, "max_turns must be in [1, 120] in this build (depth stack in shared memory)");
+  cudaError_t ce = cudaSetDevice(cfg->device);
+  if (ce != cudaSuccess) return fail(AR_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
+  e->device = cfg->device;
+  e->n_slots = cfg->concurrent_games;
+  uint32_t pn = cfg->pool_nodes;
+  if (pn == 0) pn = std::min<uint64_t>(65535u, (uint64_t)cfg->max_simulations * 12 + 1024);
+  if (pn < 64 || pn > 65535) return fail(AR_ERR_INVALID_ARG, "pool_nodes must be in [64, 65535]");
+  e->pool_nodes = pn;
+  e->max_depth = cfg->max_turns + 1;
+  e->path_stride = e->max_depth + 1;
+  e->batch_cap = cfg->max_batch_size;
+  size_t smem = 4 * warp_smem_bytes(e->max_depth, e->batch_cap);
+  if (smem > 227 * 1024) return fail(AR_ERR_UNSUPPORTED, "max_turns/max_batch_size need more than 227 KB of shared memory");
+#define CKC(call)                                                                      \
+  do {                                                                                 \
+    cudaError_t _e = (call);                                                           \
+    if (_e != cudaSuccess) return fail(AR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+  CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CKC(cudaEventCreate(&e->ev0));
+  CKC(cudaEventCreate(&e->ev1));
+  CKC(cudaMalloc(&e->pools, (size_t)e->n_slots * pn * sizeof(NodeRec)));
+  CKC(cudaMalloc(&e->path_bufs, (size_t)e->n_slots * e->batch_cap * e->path_stride * sizeof(uint32_t)));
+  CKC(cudaMalloc(&e->remaps, (size_t)e->n_slots * pn * sizeof(uint16_t)));
+  CKC(cudaMalloc(&e->coll_table, (size_t)(pn + 1) * sizeof(uint16_t)));
+  CKC(cudaMalloc(&e->d_next, sizeof(unsigned int)));
+  CKC(cudaMalloc(&e->d_counters, 8 * sizeof(unsigned long long)));
+  CKC(cudaMalloc(&e->d_error, sizeof(int)));
+  CKC(cudaHostAlloc(&e->h_progress, sizeof(ar_progress), cudaHostAllocMapped));
+  CKC(cudaHostGetDevicePointer(&e->d_progress, e->h_progress, 0));
+  CKC(cudaFuncSetAttribute(selfplay_uniform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#undef CKC
+  *out = e;
+  return AR_OK;
+}
+
+void ar_engine_destroy(ar_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaFree(e->pools); cudaFree(e->path_bufs); cudaFree(e->remaps); cudaFree(e->coll_table);
+  cudaFree(e->d_games); cudaFree(e->d_seeds); cudaFree(e->d_summaries); cudaFree(e->d_positions);
+  cudaFree(e->d_search); cudaFree(e->d_next); cudaFree(e->d_counters); cudaFree(e->d_error);
+  if (e->h_progress) cudaFreeHost(e->h_progress);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+ar_status ar_engine_load_weights(ar_engine* e, int32_t arch, int32_t, int32_t, const ar_tensor_desc*, int32_t) {
+  if (!e) return AR_ERR_INVALID_ARG;
+  if (arch == AR_ARCH_UNIFORM) return AR_OK;
+  e->err = "NN evaluators are not built into this library yet";
+  return AR_ERR_UNSUPPORTED;
+}
+
+static RunParams make_params(ar_engine* e, const ar_search_cfg* cfg) {
+  RunParams p{};
+  p.sp.c_puct = cfg->c_puct;
+  p.sp.fpu_reduction = cfg->fpu_reduction;
+  p.sp.force_k = cfg->force_k;
+  p.sp.noise_epsilon = cfg->noise_epsilon;
+  p.sp.noise_concentration = cfg->noise_concentration;
+  p.sp.n_sims = cfg->simulations;
+  p.sp.batch_size = cfg->batch_size;
+  p.pools = e->pools;
+  p.pool_nodes = e->pool_nodes;
+  p.path_bufs = e->path_bufs;
+  p.path_stride = e->path_stride;
+  p.remaps = e->remaps;
+  p.coll_table = e->coll_table;
+  p.coll_table_len = e->pool_nodes + 1;
+  p.max_depth = e->max_depth;
+  p.batch_cap = e->batch_cap;
+  p.n_slots = e->n_slots;
+  p.next_game = e->d_next;
+  p.counters = e->d_counters;
+  p.error_flag = e->d_error;
+  return p;
+}
+
+static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_progress, float* ms) {
+  CK(cudaMemsetAsync(e->d_next, 0, sizeof(unsigned int), e->stream));
+  CK(cudaMemsetAsync(e->d_counters, 0, 8 * sizeof(unsigned long long), e->stream));
+  CK(cudaMemsetAsync(e->d_error, 0, sizeof(int), e->stream));
+  memset((void*)e->h_progress, 0, sizeof(ar_progress));
+  p.progress = user_progress ? e->d_progress : nullptr;
+  size_t smem = 4 * warp_smem_bytes(e->max_depth, e->batch_cap);
+  int slots = std::min<int>(e->n_slots, std::max(p.n_games, 1));
+  p.n_slots = slots;
+  int blocks = (slots + 3) / 4;
+  CK(cudaEventRecord(e->ev0, e->stream));
+  selfplay_uniform_kernel<<<blocks, 128, smem, e->stream>>>(p);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(e->ev1, e->stream));
+  e->launches += 1;
+  if (user_progress) {
+    while (cudaEventQuery(e->ev1) == cudaErrorNotReady) {
+      memcpy((void*)user_progress, (const void*)e->h_progress, sizeof(ar_progress));
+      std::this_thread::sleep_for(std::chrono::milliseconds(2));
+    }
+  }
+  CK(cudaStreamSynchronize(e->stream));
+  if (user_progress) memcpy((void*)user_progress, (const void*)e->h_progress, sizeof(ar_progress));
+  CK(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+  int herr = 0;
+  CK(cudaMemcpy(&herr, e->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+  if (herr != 0) {
+    e->err = "device reported status " + std::to_string(herr) +
+             (herr == AR_ERR_POOL_OVERFLOW ? " (node pool / depth stack exhausted: raise pool_nodes or max_turns)" : "");
+    return (ar_status)herr;
+  }
+  return AR_OK;
+}
+
+ar_status ar_search_batch(ar_engine* e, const ar_game_pod* games, int32_t n, const ar_search_cfg* cfg,
+                          const uint64_t* seeds, ar_search_result* out) {
+  if (!e) return AR_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  ar_status s = validate_cfg(e, cfg);
+  if (s) return s;
+  s = validate_games(e, games, n);
+  if (s) return s;
+  if (n == 0) return AR_OK;
+  if (!seeds || !out) { e->err = "seeds/out is NULL"; return AR_ERR_INVALID_ARG; }
+  if ((uint64_t)cfg->simulations + 2 > e->pool_nodes) { e->err = "simulations exceed pool_nodes"; return AR_ERR_POOL_OVERFLOW; }
+  s = ensure_coll_table(e, *cfg);
+  if (s) return s;
+  if (n > e->cap_games) {
+    cudaFree(e->d_games); cudaFree(e->d_seeds); cudaFree(e->d_summaries);
+    e->d_games = nullptr; e->d_seeds = nullptr; e->d_summaries = nullptr;
+    CK(cudaMalloc(&e->d_games, (size_t)n * sizeof(ar_game_pod)));
+    CK(cudaMalloc(&e->d_seeds, (size_t)n * sizeof(uint64_t)));
+    CK(cudaMalloc(&e->d_summaries, (size_t)n * sizeof(ar_game_summary)));
+    e->cap_games = n;
+    e->cap_stride = 0;
+  }
+  if (n > e->cap_search) {
+    cudaFree(e->d_search);
+    e->d_search = nullptr;
+    CK(cudaMalloc(&e->d_search, (size_t)n * sizeof(ar_search_result)));
+    e->cap_search = n;
+  }
+  CK(cudaMemcpyAsync(e->d_games, games, (size_t)n * sizeof(ar_game_pod), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->d_seeds, seeds, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+  RunParams p = make_params(e, cfg);
+  p.games = e->d_games; p.seeds = e->d_seeds; p.n_games = n;
+  p.search_only = 1; p.search_out = e->d_search;
+  float ms = 0;
+  s = launch_and_wait(e, p, nullptr, &ms);
+  if (s) return s;
+  CK(cudaMemcpy(out, e->d_search, (size_t)n * sizeof(ar_search_result), cudaMemcpyDeviceToHost));
+  return AR_OK;
+}
+
+ar_status ar_selfplay_upload(ar_engine* e, const ar_game_pod* games, int32_t n, const uint64_t* seeds) {
+  if (!e) return AR_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  ar_status s = validate_games(e, games, n);
+  if (s) return s;
+  if (n > 0 && !seeds) { e->err = "seeds is NULL"; return AR_ERR_INVALID_ARG; }
+  int stride = 1;
+  for (int i = 0; i < n; ++i) stride = std::max<int>(stride, games[i].max_turns);
+  if (n > e->cap_games || stride > e->cap_stride) {
+    cudaFree(e->d_games); cudaFree(e->d_seeds); cudaFree(e->d_summaries); cudaFree(e->d_positions);
+    e->d_games = nullptr; e->d_seeds = nullptr; e->d_summaries = nullptr; e->d_positions = nullptr;
+    int cap = std::max(n, 1);
+    CK(cudaMalloc(&e->d_games, (size_t)cap * sizeof(ar_game_pod)));
+    CK(cudaMalloc(&e->d_seeds, (size_t)cap * sizeof(uint64_t)));
+    CK(cudaMalloc(&e->d_summaries, (size_t)cap * sizeof(ar_game_summary)));
+    CK(cudaMalloc(&e->d_positions, (size_t)cap * stride * sizeof(ar_position_record)));
+    e->cap_games = cap;
+    e->cap_stride = stride;
+  }
+  if (n > 0) {
+    CK(cudaMemcpyAsync(e->d_games, games, (size_t)n * sizeof(ar_game_pod), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_seeds, seeds, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  }
+  e->h_games.assign(games, games + n);
+  e->n_resident = n;
+  e->resident_stride = e->cap_stride;
+  e->h2d += (uint64_t)n * (sizeof(ar_game_pod) + sizeof(uint64_t));
+  return AR_OK;
+}
+
+static ar_status run_resident(ar_engine* e, const ar_search_cfg* cfg, ar_progress* progress, ar_stats* stats) {
+  ar_status s = validate_cfg(e, cfg);
+  if (s) return s;
+  s = ensure_coll_table(e, *cfg);
+  if (s) return s;
+  int n = e->n_resident;
+  float ms = 0;
+  RunParams p = make_params(e, cfg);
+  if (n > 0) {
+    p.games = e->d_games; p.seeds = e->d_seeds; p.n_games = n;
+    p.summaries = e->d_summaries; p.positions = e->d_positions; p.pos_stride = e->resident_stride;
+    p.search_only = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    s = launch_and_wait(e, p, progress, &ms);
+    if (s) return s;
+    if (stats) stats->elapsed_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  if (stats) {
+    unsigned long long c[8] = {0};
+    if (n > 0) CK(cudaMemcpy(c, e->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+    stats->device_ms = ms;
+    stats->path_nodes = c[0];
+    stats->new_nodes = c[1];
+    stats->kernel_launches = n > 0 ? 1 : 0;
+  }
+  return AR_OK;
+}
+
+ar_status ar_selfplay_run_resident(ar_engine* e, const ar_search_cfg* cfg, ar_stats* stats) {
+  if (!e) return AR_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  if (stats) memset(stats, 0, sizeof(*stats));
+  return run_resident(e, cfg, nullptr, stats);
+}
+
+// compute_cheese_outcomes (selfplay.rs:415-471) on the host from the downloaded records
+static void attribute_cheese(const ar_game_pod& pod, ar_game_summary& s, const ar_position_record* pos) {
+  int w = pod.width, cells = pod.width * pod.height;
+  int fp1 = s.reserved[0], fp2 = s.reserved[1];
+  uint64_t final_cheese;
+  memcpy(&final_cheese, s.cheese_outcomes, 8);
+  memset(s.cheese_outcomes, 2, sizeof(s.cheese_outcomes));
+  memset(s.reserved, 0, sizeof(s.reserved));
+  int n = (int)s.n_positions;
+  for (int i = 0; i < n; ++i) {
+    uint64_t cur, nxt;
+    memcpy(&cur, pos[i].cheese, 8);
+    int n1, n2;
+    if (i + 1 < n) {
+      memcpy(&nxt, pos[i + 1].cheese, 8);
+      n1 = pos[i + 1].p1_y * w + pos[i + 1].p1_x;
+      n2 = pos[i + 1].p2_y * w + pos[i + 1].p2_x;
+    } else {
+      nxt = final_cheese; n1 = fp1; n2 = fp2;
+    }
+    uint64_t gone = cur & ~nxt;
+    for (int c = 0; c < cells; ++c)
+      if ((gone >> c) & 1) {
+        bool a = n1 == c, b = n2 == c;
+        s.cheese_outcomes[c] = (a && b) ? 1 : a ? 0 : b ? 3 : 2;
+      }
+  }
+}
+
+ar_status ar_selfplay_download(ar_engine* e, ar_game_summary* summaries, ar_position_record* positions,
+                               int32_t positions_stride) {
+  if (!e) return AR_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  int n = e->n_resident;
+  if (n == 0) return AR_OK;
+  if (!summaries || !positions) { e->err = "summaries/positions is NULL"; return AR_ERR_INVALID_ARG; }
+  if (positions_stride < 1) { e->err = "positions_stride < 1"; return AR_ERR_INVALID_ARG; }
+  CK(cudaMemcpy(summaries, e->d_summaries, (size_t)n * sizeof(ar_game_summary), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i)
+    if ((int)summaries[i].n_positions > positions_stride) {
+      e->err = "positions_stride smaller than a game's length";
+      return AR_ERR_INVALID_ARG;
+    }
+  int copy_w = std::min(positions_stride, e->resident_stride);
+  CK(cudaMemcpy2D(positions, (size_t)positions_stride * sizeof(ar_position_record), e->d_positions,
+                  (size_t)e->resident_stride * sizeof(ar_position_record),
+                  (size_t)copy_w * sizeof(ar_position_record), n, cudaMemcpyDeviceToHost));
+  e->d2h += (uint64_t)n * (sizeof(ar_game_summary) + (size_t)copy_w * sizeof(ar_position_record));
+  for (int i = 0; i < n; ++i)
+    attribute_cheese(e->h_games[i], summaries[i], positions + (size_t)i * positions_stride);
+  return AR_OK;
+}
+
+ar_status ar_selfplay_run(ar_engine* e, const ar_game_pod* games, int32_t n, const ar_search_cfg* cfg,
+                          const uint64_t* seeds, ar_game_summary* summaries, ar_position_record* positions,
+                          int32_t positions_stride, ar_progress* progress, ar_stats* stats) {
+  if (!e) return AR_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  auto t0 = std::chrono::steady_clock::now();
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (progress) memset((void*)progress, 0, sizeof(*progress));
+  e->h2d = e->d2h = 0;
+  ar_status s = validate_cfg(e, cfg);
+  if (s) return s;
+  s = ar_selfplay_upload(e, games, n, seeds);
+  if (s) return s;
+  s = run_resident(e, cfg, progress, stats);
+  if (s) return s;
+  s = ar_selfplay_download(e, summaries, positions, positions_stride);
+  if (s) return s;
+  if (stats) {  // SelfPlayStats::from_games, selfplay.rs:212-224
+    stats->min_turns = 0xffffffffu;
+    for (int i = 0; i < n; ++i) {
+      const ar_game_summary& g = summaries[i];
+      stats->total_games += 1;
+      stats->total_positions += g.n_positions;
+      stats->total_simulations += g.total_simulations;
+      stats->total_nn_evals += g.total_nn_evals;
+      stats->total_terminals += g.total_terminals;
+      stats->total_collisions += g.total_collisions;
+      stats->total_cheese_collected += g.final_p1_score + g.final_p2_score;
+      stats->total_cheese_available += g.cheese_available;
+      stats->min_turns = std::min(stats->min_turns, g.n_positions);
+      stats->max_turns = std::max(stats->max_turns, g.n_positions);
+      if (g.result == 1) stats->p1_wins++; else if (g.result == 2) stats->p2_wins++; else stats->draws++;
+    }
+    if (n == 0) stats->min_turns = 0;
+    stats->elapsed_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    stats->h2d_bytes = e->h2d;
+    stats->d2h_bytes = e->d2h;
+  }
+  return AR_OK;
+}
+
+ar_status ar_encode_observations(ar_engine* e, const ar_game_pod*, int32_t, float*) {
+  if (!e) return AR_ERR_INVALID_ARG;
+  e->err = "ar_encode_observations: NN path not built yet";
+  return AR_ERR_UNSUPPORTED;
+}
+
+ar_status ar_nn_forward(ar_engine* e, const ar_game_pod*, int32_t, float*, float*, float*, float*) {
+  if (!e) return AR_ERR_INVALID_ARG;
+  e->err = "ar_nn_forward: NN path not built yet";
+  return AR_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+"""Thin object wrapper over the C-ABI engine handle (include/alpharat_cuda.h)."""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _native as N
+
+_STATUS_EXC = {
+    N.AR_ERR_INVALID_ARG: ValueError,
+    N.AR_ERR_CUDA: RuntimeError,
+    N.AR_ERR_POOL_OVERFLOW: RuntimeError,
+    N.AR_ERR_NONFINITE: RuntimeError,
+    N.AR_ERR_UNSUPPORTED: NotImplementedError,
+    N.AR_ERR_NO_WEIGHTS: RuntimeError,
+}
+
+
+def search_cfg(*, simulations: int, batch_size: int = 8, c_puct: float = 1.5, fpu_reduction: float = 0.2,
+               force_k: float = 2.0, noise_epsilon: float = 0.0, noise_concentration: float = 10.83,
+               collision_limit_min: int = 1, collision_limit_max: int = 256,
+               collision_scaling_start: int = 800, collision_scaling_end: int = 50_000,
+               collision_scaling_power: float = 1.0) -> N.SearchCfg:
+    return N.SearchCfg(simulations, batch_size, c_puct, fpu_reduction, force_k, noise_epsilon,
+                       noise_concentration, collision_limit_min, collision_limit_max,
+                       collision_scaling_start, collision_scaling_end, collision_scaling_power)
+
+
+class Engine:
+    """One engine per GPU; single-threaded handle (see header)."""
+
+    def __init__(self, *, device: int = 0, concurrent_games: int = 4096, pool_nodes: int = 0,
+                 max_cells: int = 64, max_turns: int = 64, max_batch_size: int = 16,
+                 max_simulations: int = 2048) -> None:
+        self._lib = N.load_library()
+        cfg = N.EngineCfg(N.AR_ABI_VERSION, device, concurrent_games, pool_nodes, max_cells,
+                          max_turns, max_batch_size, max_simulations)
+        handle = C.c_void_p()
+        st = self._lib.ar_engine_create(C.byref(cfg), C.byref(handle))
+        if st != N.AR_OK:
+            msg = self._lib.ar_last_error(None)
+            raise _STATUS_EXC.get(st, RuntimeError)(f"ar_engine_create failed ({st}): {msg.decode() if msg else ''}")
+        self._h = handle
+        self.cfg = cfg
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.ar_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self) -> "Engine":
+        return self
+
+    def __exit__(self, *exc) -> None:
+        self.close()
+
+    def _check(self, st: int, what: str) -> None:
+        if st != N.AR_OK:
+            msg = self._lib.ar_last_error(self._h)
+            raise _STATUS_EXC.get(st, RuntimeError)(f"{what} failed ({st}): {msg.decode() if msg else ''}")
+
+    # --- evaluator -----------------------------------------------------------------------
+    def load_weights(self, arch: int, width: int, height: int, tensors: dict[str, np.ndarray]) -> None:
+        keep = []
+        descs = (N.TensorDesc * max(len(tensors), 1))()
+        for i, (name, arr) in enumerate(tensors.items()):
+            a = np.ascontiguousarray(arr, dtype=np.float32)
+            keep.append(a)
+            descs[i].name = name.encode()
+            descs[i].data = a.ctypes.data_as(C.POINTER(C.c_float))
+            descs[i].ndim = a.ndim
+            for d in range(4):
+                descs[i].shape[d] = a.shape[d] if d < a.ndim else 1
+        self._check(self._lib.ar_engine_load_weights(self._h, arch, width, height, descs, len(tensors)),
+                    "ar_engine_load_weights")
+
+    # --- search ----------------------------------------------------------------------------
+    def search_batch(self, pods, cfg: N.SearchCfg, seeds: Sequence[int]):
+        n = len(pods)
+        out = (N.SearchResultPod * max(n, 1))()
+        sd = (C.c_uint64 * max(n, 1))(*[int(s) & ((1 << 64) - 1) for s in seeds])
+        self._check(self._lib.ar_search_batch(self._h, pods, n, C.byref(cfg), sd, out), "ar_search_batch")
+        return out
+
+    # --- self-play ---------------------------------------------------------------------------
+    def selfplay(self, pods, cfg: N.SearchCfg, seeds: Sequence[int], *, stride: int | None = None,
+                 progress: N.Progress | None = None):
+        n = len(pods)
+        if stride is None:
+            stride = max([p.max_turns for p in pods] + [1])
+        summaries = (N.GameSummary * max(n, 1))()
+        positions = (N.PositionRecord * max(n * stride, 1))()
+        stats = N.Stats()
+        sd = (C.c_uint64 * max(n, 1))(*[int(s) & ((1 << 64) - 1) for s in seeds])
+        pr = C.byref(progress) if progress is not None else None
+        self._check(self._lib.ar_selfplay_run(self._h, pods, n, C.byref(cfg), sd, summaries, positions,
+                                              stride, pr, C.byref(stats)), "ar_selfplay_run")
+        return summaries, positions, stride, stats
+
+    def selfplay_upload(self, pods, seeds: Sequence[int]) -> None:
+        n = len(pods)
+        sd = (C.c_uint64 * max(n, 1))(*[int(s) & ((1 << 64) - 1) for s in seeds])
+        self._check(self._lib.ar_selfplay_upload(self._h, pods, n, sd), "ar_selfplay_upload")
+
+    def selfplay_run_resident(self, cfg: N.SearchCfg) -> N.Stats:
+        stats = N.Stats()
+        self._check(self._lib.ar_selfplay_run_resident(self._h, C.byref(cfg), C.byref(stats)),
+                    "ar_selfplay_run_resident")
+        return stats
+
+    def selfplay_download(self, n: int, stride: int):
+        summaries = (N.GameSummary * max(n, 1))()
+        positions = (N.PositionRecord * max(n * stride, 1))()
+        self._check(self._lib.ar_selfplay_download(self._h, summaries, positions, stride), "ar_selfplay_download")
+        return summaries, positions
+
+    # --- evaluator entry points ------------------------------------------------------------
+    def encode(self, pods) -> np.ndarray:
+        n = len(pods)
+        dim = 7 * pods[0].width * pods[0].height + 6 if n else 0
+        out = np.zeros((n, dim), dtype=np.float32)
+        self._check(self._lib.ar_encode_observations(self._h, pods, n, out.ctypes.data_as(C.POINTER(C.c_float))),
+                    "ar_encode_observations")
+        return out
+
+    def nn_forward(self, pods):
+        n = len(pods)
+        p1 = np.zeros((n, 5), np.float32)
+        p2 = np.zeros((n, 5), np.float32)
+        v1 = np.zeros(n, np.float32)
+        v2 = np.zeros(n, np.float32)
+        f = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        self._check(self._lib.ar_nn_forward(self._h, pods, n, f(p1), f(p2), f(v1), f(v2)), "ar_nn_forward")
+        return p1, p2, v1, v2

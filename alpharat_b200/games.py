@@ -1,0 +1,208 @@
+"""Game construction for the CUDA backend: `ar_game_pod` packing and a game generator.
+
+Mirrors what the reference does inside Rust before self-play starts
+(`make_games`, crates/alpharat-sampling/src/bindings.rs:489-533) and what `rust_mcts_search`
+reads from a `PyRat` object (crates/alpharat-mcts/src/bindings.rs:250).  The third-party
+engine's random generators are not available offline, so layouts come from this module's own
+documented generator: open maze (or explicit walls/mud), corner starts, cheese
+drawn without replacement with optional 180-degree rotational symmetry, PRNG = SplitMix64 keyed
+by the game index.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Any, Iterable, Sequence
+
+import numpy as np
+
+from ._native import AR_MAX_CELLS, GamePod
+
+UP, RIGHT, DOWN, LEFT, STAY = 0, 1, 2, 3, 4
+_DELTA = {UP: (0, 1), RIGHT: (1, 0), DOWN: (0, -1), LEFT: (-1, 0)}
+_MASK64 = (1 << 64) - 1
+
+
+class SplitMix64:
+    """SplitMix64 stream (the generator's only source of randomness)."""
+
+    def __init__(self, seed: int) -> None:
+        self.state = seed & _MASK64
+
+    def next(self) -> int:
+        self.state = (self.state + 0x9E3779B97F4A7C15) & _MASK64
+        z = self.state
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _MASK64
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _MASK64
+        return z ^ (z >> 31)
+
+    def below(self, n: int) -> int:
+        return self.next() % n
+
+
+@dataclass
+class GameSpec:
+    """Explicit description of one PyRat position (host-side twin of `ar_game_pod`)."""
+
+    width: int
+    height: int
+    max_turns: int
+    p1: tuple[int, int]
+    p2: tuple[int, int]
+    cheese: Sequence[tuple[int, int]]
+    walls: Sequence[tuple[tuple[int, int], tuple[int, int]]] = field(default_factory=list)
+    mud: Sequence[tuple[tuple[int, int], tuple[int, int], int]] = field(default_factory=list)
+    turn: int = 0
+    p1_score: float = 0.0
+    p2_score: float = 0.0
+    p1_mud: int = 0
+    p2_mud: int = 0
+
+
+def _direction(a: tuple[int, int], b: tuple[int, int]) -> int:
+    d = (b[0] - a[0], b[1] - a[1])
+    for k, v in _DELTA.items():
+        if v == d:
+            return k
+    raise ValueError(f"cells {a} and {b} are not adjacent")
+
+
+def move_cost_table(width: int, height: int, walls: Iterable = (), mud: Iterable = ()) -> np.ndarray:
+    """u8[cells*4]: 0 = wall/boundary, 1 = open, c >= 2 = mud cost (cell = y*width + x)."""
+    t = np.ones((height, width, 4), dtype=np.uint8)
+    t[:, 0, LEFT] = 0
+    t[:, width - 1, RIGHT] = 0
+    t[0, :, DOWN] = 0
+    t[height - 1, :, UP] = 0
+    for a, b in walls:
+        d = _direction(tuple(a), tuple(b))
+        t[a[1], a[0], d] = 0
+        t[b[1], b[0], (d + 2) % 4] = 0
+    for a, b, v in mud:
+        d = _direction(tuple(a), tuple(b))
+        t[a[1], a[0], d] = v
+        t[b[1], b[0], (d + 2) % 4] = v
+    return t.reshape(-1)
+
+
+def pack_pod(spec: GameSpec, out: GamePod | None = None) -> GamePod:
+    cells = spec.width * spec.height
+    if cells > AR_MAX_CELLS:
+        raise ValueError(f"{spec.width}x{spec.height} exceeds AR_MAX_CELLS={AR_MAX_CELLS}")
+    pod = out if out is not None else GamePod()
+    C.memset(C.byref(pod), 0, C.sizeof(pod))
+    pod.width, pod.height = spec.width, spec.height
+    pod.p1_x, pod.p1_y = spec.p1
+    pod.p2_x, pod.p2_y = spec.p2
+    pod.p1_mud, pod.p2_mud = spec.p1_mud, spec.p2_mud
+    pod.turn, pod.max_turns = spec.turn, spec.max_turns
+    pod.p1_score, pod.p2_score = spec.p1_score, spec.p2_score
+    mc = move_cost_table(spec.width, spec.height, spec.walls, spec.mud)
+    C.memmove(pod.move_cost, mc.ctypes.data, mc.size)
+    for x, y in spec.cheese:
+        c = y * spec.width + x
+        pod.cheese[c >> 3] |= 1 << (c & 7)
+    return pod
+
+
+def pods_array(specs: Sequence[GameSpec]):
+    arr = (GamePod * len(specs))()
+    for i, s in enumerate(specs):
+        pack_pod(s, arr[i])
+    return arr
+
+
+def pod_from_pyrat(game: Any) -> GamePod:
+    """Pack a duck-typed `PyRat` (CLAUDE.md "PyRat Game API") into an `ar_game_pod`."""
+
+    def xy(p: Any) -> tuple[int, int]:
+        return (int(p.x), int(p.y)) if hasattr(p, "x") else (int(p[0]), int(p[1]))
+
+    spec = GameSpec(
+        width=int(game.width),
+        height=int(game.height),
+        max_turns=int(game.max_turns),
+        p1=xy(game.player1_position),
+        p2=xy(game.player2_position),
+        cheese=[xy(c) for c in game.cheese_positions()],
+        walls=[(xy(w.pos1), xy(w.pos2)) for w in game.wall_entries()],
+        mud=[(xy(m.pos1), xy(m.pos2), int(m.value)) for m in game.mud_entries()],
+        turn=int(game.turn),
+        p1_score=float(game.player1_score),
+        p2_score=float(game.player2_score),
+        p1_mud=int(game.player1_mud_turns),
+        p2_mud=int(game.player2_mud_turns),
+    )
+    return pack_pod(spec)
+
+
+def random_cheese(width: int, height: int, count: int, symmetric: bool, rng: SplitMix64,
+                  exclude: Iterable[tuple[int, int]]) -> list[tuple[int, int]]:
+    """`count` distinct cells, none in `exclude`; 180-degree symmetric pairs when asked."""
+    excl = set(exclude)
+    chosen: list[tuple[int, int]] = []
+    taken = set(excl)
+    centre = ((width - 1) / 2, (height - 1) / 2)
+    has_centre = width % 2 == 1 and height % 2 == 1
+    centre_cell = (width // 2, height // 2)
+    if symmetric:
+        if count % 2 == 1:
+            if not has_centre or centre_cell in taken:
+                raise ValueError("odd symmetric cheese count needs a free centre cell")
+            chosen.append(centre_cell)
+            taken.add(centre_cell)
+        while len(chosen) < count:
+            c = rng.below(width * height)
+            p = (c % width, c // width)
+            q = (width - 1 - p[0], height - 1 - p[1])
+            if p in taken or q in taken or p == q or (p[0], p[1]) == centre:
+                continue
+            chosen += [p, q]
+            taken.update((p, q))
+    else:
+        while len(chosen) < count:
+            c = rng.below(width * height)
+            p = (c % width, c // width)
+            if p in taken:
+                continue
+            chosen.append(p)
+            taken.add(p)
+    return chosen
+
+
+def make_games(
+    num_games: int,
+    *,
+    width: int,
+    height: int,
+    cheese_count: int,
+    max_turns: int,
+    cheese_symmetric: bool = True,
+    maze_type: str = "open",
+    positions: str = "corners",
+    first_index: int = 0,
+) -> list[GameSpec]:
+    """Generator behind `cuda_self_play` (same axes as `make_games`, bindings.rs:489-533).
+
+    Only `maze_type="open"` / `positions="corners"` are generated here; walls and mud are
+    accepted through explicit `GameSpec`s (`games=` argument of `cuda_self_play`).
+    """
+    if maze_type != "open":
+        raise ValueError(f"maze_type={maze_type!r}: only 'open' is generated; pass games= explicitly")
+    if positions != "corners":
+        raise ValueError(f"positions={positions!r}: only 'corners' is generated; pass games= explicitly")
+    p1, p2 = (0, 0), (width - 1, height - 1)
+    out = []
+    for i in range(num_games):
+        rng = SplitMix64(first_index + i)
+        cheese = random_cheese(width, height, cheese_count, cheese_symmetric, rng, (p1, p2))
+        out.append(GameSpec(width, height, max_turns, p1, p2, cheese))
+    return out
+
+
+def maze_array(spec: GameSpec) -> np.ndarray:
+    """i8[H, W, 4]: -1 wall, 1 open, >= 2 mud (build_maze_array, selfplay.rs:374-392)."""
+    mc = move_cost_table(spec.width, spec.height, spec.walls, spec.mud).astype(np.int16)
+    mc[mc == 0] = -1
+    return mc.astype(np.int8).reshape(spec.height, spec.width, 4)
