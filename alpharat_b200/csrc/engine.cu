@@ -201,8 +201,10 @@ __global__ void __launch_bounds__(128, 4) selfplay_uniform_kernel(RunParams p) {
         pr.action_p1 = (uint8_t)a1; pr.action_p2 = (uint8_t)a2;
         pr.turn = (uint16_t)turn; pr.reserved = 0;
         pr.p1_score = 0.5f * (float)g.s1x2; pr.p2_score = 0.5f * (float)g.s2x2;
-        uint64_t* cb = reinterpret_cast<uint64_t*>(pr.cheese);
-        cb[0] = g.cheese; cb[1] = 0; cb[2] = 0; cb[3] = 0;
+        uint32_t* cb = reinterpret_cast<uint32_t*>(pr.cheese);  // 4-byte aligned only
+        cb[0] = (uint32_t)g.cheese; cb[1] = (uint32_t)(g.cheese >> 32);
+#pragma unroll
+        for (int t = 2; t < 8; ++t) cb[t] = 0;
       }
       n_pos += 1;
 
