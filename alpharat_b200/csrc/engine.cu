@@ -37,9 +37,11 @@ struct RunParams {
   // per-slot storage
   NodeRec* pools;
   uint32_t pool_nodes;
-  uint32_t* path_bufs;
+  uint2* path_bufs;
   uint32_t path_stride;
-  uint16_t* remaps;
+  uint32_t* remaps;
+  Level* spill_levels;
+  uint32_t spill_depth;
   const uint16_t* coll_table;
   uint32_t coll_table_len;
   uint32_t max_depth;
@@ -53,7 +55,8 @@ struct RunParams {
 };
 
 __host__ __device__ inline size_t warp_smem_bytes(uint32_t max_depth, uint32_t batch_cap) {
-  size_t b = (size_t)max_depth * sizeof(Level);      // level stack
+  (void)max_depth;
+  size_t b = (size_t)SMEM_LEVELS * sizeof(Level);    // level stack (deeper levels spill)
   b += (size_t)batch_cap * sizeof(GState);           // leaf states
   b += 256;                                          // maze cost table (64 cells x 4)
   b += (size_t)batch_cap * sizeof(TpEntry);          // batch entries
@@ -132,12 +135,13 @@ __global__ void __launch_bounds__(128, 4) selfplay_uniform_kernel(RunParams p) {
   uint8_t* base = smem + (size_t)wib * warp_smem_bytes(p.max_depth, p.batch_cap);
   WarpCtx cx;
   cx.levels = reinterpret_cast<Level*>(base);
-  cx.tp_state = reinterpret_cast<GState*>(base + (size_t)p.max_depth * sizeof(Level));
+  cx.tp_state = reinterpret_cast<GState*>(base + (size_t)SMEM_LEVELS * sizeof(Level));
   cx.maze = reinterpret_cast<uint8_t*>(cx.tp_state + p.batch_cap);
   cx.tp = reinterpret_cast<TpEntry*>(cx.maze + 256);
   cx.pool = p.pools + (size_t)slot * p.pool_nodes;
   cx.path_buf = p.path_bufs + (size_t)slot * p.batch_cap * p.path_stride;
   cx.remap = p.remaps + (size_t)slot * p.pool_nodes;
+  cx.spill_levels = p.spill_levels + (size_t)slot * p.spill_depth;
   cx.coll_table = p.coll_table;
   cx.pool_nodes = p.pool_nodes;
   cx.path_stride = p.path_stride;
@@ -209,9 +213,9 @@ __global__ void __launch_bounds__(128, 4) selfplay_uniform_kernel(RunParams p) {
       n_pos += 1;
 
       // advance_root maps raw actions through action_to_outcome_idx (tree.rs:283-295)
-      uint32_t rmeta = cx.pool[0].v[11].y;
+      uint32_t rmeta = cx.pool[0].s[LANE_LINKS].y;
       int i = action_to_idx(meta_m1(rmeta), a1), j = action_to_idx(meta_m2(rmeta), a2);
-      uint32_t child = reinterpret_cast<const uint16_t*>(&cx.pool[0].v[12])[i * 5 + j];
+      uint32_t child = reinterpret_cast<const uint32_t*>(&cx.pool[0].s[LANE_CHILD])[i * 5 + j];
       game_step(g, a1, a2, cx.maze, cx.w);
       turn += 1;
       __syncwarp();
@@ -269,11 +273,14 @@ struct ar_engine {
   std::string err;
   // per-slot storage
   NodeRec* pools = nullptr;
-  uint32_t* path_bufs = nullptr;
-  uint16_t* remaps = nullptr;
+  uint2* path_bufs = nullptr;
+  uint32_t* remaps = nullptr;
+  Level* spill_levels = nullptr;
+  uint32_t spill_depth = 0;
   uint16_t* coll_table = nullptr;
   uint32_t pool_nodes = 0, path_stride = 0, max_depth = 0, batch_cap = 0, n_slots = 0;
   ar_search_cfg coll_cfg{};
+  uint32_t coll_len = 0;
   bool coll_valid = false;
   // run buffers
   ar_game_pod* d_games = nullptr;
@@ -320,8 +327,13 @@ static ar_status ensure_coll_table(ar_engine* e, const ar_search_cfg& c) {
   if (e->coll_valid && memcmp(&e->coll_cfg.collision_limit_min, &c.collision_limit_min,
                               sizeof(uint32_t) * 4 + sizeof(float)) == 0)
     return AR_OK;
-  std::vector<uint16_t> t(e->pool_nodes + 1);
-  for (uint32_t n = 0; n <= e->pool_nodes; ++n) {
+  // beyond collision_scaling_end the budget is constant, so the table may be clamped
+  if (c.collision_scaling_end >= e->coll_len && e->pool_nodes + 1 > e->coll_len) {
+    e->err = "collision_scaling_end beyond the collision table";
+    return AR_ERR_UNSUPPORTED;
+  }
+  std::vector<uint16_t> t(e->coll_len);
+  for (uint32_t n = 0; n < e->coll_len; ++n) {
     uint32_t v = host_collisions_left(n, c);
     t[n] = (uint16_t)std::min<uint32_t>(v, 65535u);
   }
@@ -345,7 +357,14 @@ static ar_status validate_cfg(ar_engine* e, const ar_search_cfg* c) {
     e->err = "noise_epsilon > 0 (Dirichlet root noise) is not implemented in this build";
     return AR_ERR_UNSUPPORTED;
   }
-  if (c->collision_limit_max > 65535u) { e->err = "collision_limit_max > 65535"; return AR_ERR_INVALID_ARG; }
+  if (c->collision_limit_max + 2 * c->batch_size > 1023u) {
+    e->err = "collision_limit_max + 2 * batch_size must be <= 1023 (10-bit in-flight counters)";
+    return AR_ERR_INVALID_ARG;
+  }
+  if ((uint64_t)c->simulations * e->cfg.max_turns >= (1ull << VIS_BITS)) {
+    e->err = "simulations * max_turns must be < 2^22 (22-bit edge visit counters)";
+    return AR_ERR_INVALID_ARG;
+  }
   return AR_OK;
 }
 
@@ -392,15 +411,25 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
   if (cfg->concurrent_games == 0) return fail(AR_ERR_INVALID_ARG, "concurrent_games must be > 0");
   if (cfg->max_cells == 0 || cfg->max_cells > 64) return fail(AR_ERR_UNSUPPORTED, "max_cells must be in [1, 64] in this build");
   if (cfg->max_batch_size == 0 || cfg->max_batch_size > MAX_BATCH) return fail(AR_ERR_INVALID_ARG, "max_batch_size must be in [1, 64]");
-  if (cfg->max_turns == 0 || cfg->max_turns > 120) return fail(AR_ERR_UNSUPPORTED, "max_turns must be in [1, 120] in this build (depth stack in shared memory)");
+  if (cfg->max_turns == 0 || cfg->max_turns > 250) return fail(AR_ERR_UNSUPPORTED, "max_turns must be in [1, 250] in this build (8-bit path depth)");
   cudaError_t ce = cudaSetDevice(cfg->device);
   if (ce != cudaSuccess) return fail(AR_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
   e->device = cfg->device;
   e->n_slots = cfg->concurrent_games;
-  uint32_t pn = cfg->pool_nodes;
-  if (pn == 0) pn = std::min<uint64_t>(65535u, (uint64_t)cfg->max_simulations * 12 + 1024);
-  if (pn < 64 || pn > 65535) return fail(AR_ERR_INVALID_ARG, "pool_nodes must be in [64, 65535]");
-  e->pool_nodes = pn;
+  // Pool sizing: a tree can keep growing through tree reuse, by at most `simulations` nodes per
+  // move, so max_turns * max_simulations + 2 nodes can never overflow.  Use that when it fits in
+  // 70 % of free HBM, otherwise the largest pool that does (overflow is then a loud error).
+  uint64_t pn = cfg->pool_nodes;
+  if (pn == 0) {
+    size_t free_b = 0, total_b = 0;
+    cudaError_t me = cudaMemGetInfo(&free_b, &total_b);
+    if (me != cudaSuccess) return fail(AR_ERR_CUDA, std::string("cudaMemGetInfo: ") + cudaGetErrorString(me));
+    uint64_t worst = (uint64_t)cfg->max_turns * std::max<uint32_t>(cfg->max_simulations, 1) + 2;
+    uint64_t fit = (uint64_t)(0.70 * (double)free_b) / cfg->concurrent_games / (sizeof(NodeRec) + sizeof(uint32_t));
+    pn = std::max<uint64_t>(std::min(worst, fit), 64);
+  }
+  if (pn < 64 || pn > 0x7fffffffull) return fail(AR_ERR_INVALID_ARG, "pool_nodes must be in [64, 2^31)");
+  e->pool_nodes = (uint32_t)pn;
   e->max_depth = cfg->max_turns + 1;
   e->path_stride = e->max_depth + 1;
   e->batch_cap = cfg->max_batch_size;
@@ -414,10 +443,13 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
   CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CKC(cudaEventCreate(&e->ev0));
   CKC(cudaEventCreate(&e->ev1));
-  CKC(cudaMalloc(&e->pools, (size_t)e->n_slots * pn * sizeof(NodeRec)));
-  CKC(cudaMalloc(&e->path_bufs, (size_t)e->n_slots * e->batch_cap * e->path_stride * sizeof(uint32_t)));
-  CKC(cudaMalloc(&e->remaps, (size_t)e->n_slots * pn * sizeof(uint16_t)));
-  CKC(cudaMalloc(&e->coll_table, (size_t)(pn + 1) * sizeof(uint16_t)));
+  CKC(cudaMalloc(&e->pools, (size_t)e->n_slots * (size_t)pn * sizeof(NodeRec)));
+  CKC(cudaMalloc(&e->path_bufs, (size_t)e->n_slots * e->batch_cap * e->path_stride * sizeof(uint2)));
+  CKC(cudaMalloc(&e->remaps, (size_t)e->n_slots * pn * sizeof(uint32_t)));
+  e->spill_depth = e->max_depth > (uint32_t)SMEM_LEVELS ? e->max_depth - SMEM_LEVELS : 1;
+  CKC(cudaMalloc(&e->spill_levels, (size_t)e->n_slots * e->spill_depth * sizeof(Level)));
+  e->coll_len = (uint32_t)std::min<uint64_t>(pn + 1, 1u << 20);
+  CKC(cudaMalloc(&e->coll_table, (size_t)e->coll_len * sizeof(uint16_t)));
   CKC(cudaMalloc(&e->d_next, sizeof(unsigned int)));
   CKC(cudaMalloc(&e->d_counters, 8 * sizeof(unsigned long long)));
   CKC(cudaMalloc(&e->d_error, sizeof(int)));
@@ -433,6 +465,7 @@ void ar_engine_destroy(ar_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaFree(e->pools); cudaFree(e->path_bufs); cudaFree(e->remaps); cudaFree(e->coll_table);
+  cudaFree(e->spill_levels);
   cudaFree(e->d_games); cudaFree(e->d_seeds); cudaFree(e->d_summaries); cudaFree(e->d_positions);
   cudaFree(e->d_search); cudaFree(e->d_next); cudaFree(e->d_counters); cudaFree(e->d_error);
   if (e->h_progress) cudaFreeHost(e->h_progress);
@@ -463,8 +496,10 @@ static RunParams make_params(ar_engine* e, const ar_search_cfg* cfg) {
   p.path_bufs = e->path_bufs;
   p.path_stride = e->path_stride;
   p.remaps = e->remaps;
+  p.spill_levels = e->spill_levels;
+  p.spill_depth = e->spill_depth;
   p.coll_table = e->coll_table;
-  p.coll_table_len = e->pool_nodes + 1;
+  p.coll_table_len = e->coll_len;
   p.max_depth = e->max_depth;
   p.batch_cap = e->batch_cap;
   p.n_slots = e->n_slots;
