@@ -37,11 +37,9 @@ struct RunParams {
   // per-slot storage
   NodeRec* pools;
   uint32_t pool_nodes;
-  uint2* path_bufs;
+  uint32_t* path_bufs;
   uint32_t path_stride;
   uint32_t* remaps;
-  Level* spill_levels;
-  uint32_t spill_depth;
   const uint16_t* coll_table;
   uint32_t coll_table_len;
   uint32_t max_depth;
@@ -55,8 +53,8 @@ struct RunParams {
 };
 
 __host__ __device__ inline size_t warp_smem_bytes(uint32_t max_depth, uint32_t batch_cap) {
-  (void)max_depth;
-  size_t b = (size_t)SMEM_LEVELS * sizeof(Level);    // level stack (deeper levels spill)
+  size_t b = (size_t)max_depth * sizeof(Level);      // level stack
+  b += (size_t)(batch_cap + max_depth + 1) * sizeof(ChildEnt);  // per-level child lists
   b += (size_t)batch_cap * sizeof(GState);           // leaf states
   b += 256;                                          // maze cost table (64 cells x 4)
   b += (size_t)batch_cap * sizeof(TpEntry);          // batch entries
@@ -76,7 +74,7 @@ __device__ __forceinline__ void simulate_batch_uniform(WarpCtx& cx, const Search
   int n_tp = 0;
   while ((uint32_t)n_tp < bs && collisions_left > 0 && cx.error == 0) {
     uint32_t budget = min((uint32_t)collisions_left, bs - (uint32_t)n_tp);
-    uint32_t c = pick_nodes(cx, sp, rng, root_g, root_turn, budget, n_tp, true, lane);
+    uint32_t c = pick_nodes<false>(cx, sp, rng, root_g, root_turn, budget, n_tp, true, lane);
     collisions_left -= (int)c;
     coll += c;
   }
@@ -135,13 +133,13 @@ __global__ void __launch_bounds__(128, 4) selfplay_uniform_kernel(RunParams p) {
   uint8_t* base = smem + (size_t)wib * warp_smem_bytes(p.max_depth, p.batch_cap);
   WarpCtx cx;
   cx.levels = reinterpret_cast<Level*>(base);
-  cx.tp_state = reinterpret_cast<GState*>(base + (size_t)SMEM_LEVELS * sizeof(Level));
+  cx.cstack = reinterpret_cast<ChildEnt*>(base + (size_t)p.max_depth * sizeof(Level));
+  cx.tp_state = reinterpret_cast<GState*>(cx.cstack + (p.batch_cap + p.max_depth + 1));
   cx.maze = reinterpret_cast<uint8_t*>(cx.tp_state + p.batch_cap);
   cx.tp = reinterpret_cast<TpEntry*>(cx.maze + 256);
   cx.pool = p.pools + (size_t)slot * p.pool_nodes;
   cx.path_buf = p.path_bufs + (size_t)slot * p.batch_cap * p.path_stride;
   cx.remap = p.remaps + (size_t)slot * p.pool_nodes;
-  cx.spill_levels = p.spill_levels + (size_t)slot * p.spill_depth;
   cx.coll_table = p.coll_table;
   cx.pool_nodes = p.pool_nodes;
   cx.path_stride = p.path_stride;
@@ -273,10 +271,8 @@ struct ar_engine {
   std::string err;
   // per-slot storage
   NodeRec* pools = nullptr;
-  uint2* path_bufs = nullptr;
+  uint32_t* path_bufs = nullptr;
   uint32_t* remaps = nullptr;
-  Level* spill_levels = nullptr;
-  uint32_t spill_depth = 0;
   uint16_t* coll_table = nullptr;
   uint32_t pool_nodes = 0, path_stride = 0, max_depth = 0, batch_cap = 0, n_slots = 0;
   ar_search_cfg coll_cfg{};
@@ -428,7 +424,8 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
     uint64_t fit = (uint64_t)(0.70 * (double)free_b) / cfg->concurrent_games / (sizeof(NodeRec) + sizeof(uint32_t));
     pn = std::max<uint64_t>(std::min(worst, fit), 64);
   }
-  if (pn < 64 || pn > 0x7fffffffull) return fail(AR_ERR_INVALID_ARG, "pool_nodes must be in [64, 2^31)");
+  pn = std::min<uint64_t>(pn, (1ull << PATH_NODE_BITS) - 1);
+  if (pn < 64) return fail(AR_ERR_INVALID_ARG, "pool_nodes must be >= 64");
   e->pool_nodes = (uint32_t)pn;
   e->max_depth = cfg->max_turns + 1;
   e->path_stride = e->max_depth + 1;
@@ -444,10 +441,8 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
   CKC(cudaEventCreate(&e->ev0));
   CKC(cudaEventCreate(&e->ev1));
   CKC(cudaMalloc(&e->pools, (size_t)e->n_slots * (size_t)pn * sizeof(NodeRec)));
-  CKC(cudaMalloc(&e->path_bufs, (size_t)e->n_slots * e->batch_cap * e->path_stride * sizeof(uint2)));
+  CKC(cudaMalloc(&e->path_bufs, (size_t)e->n_slots * e->batch_cap * e->path_stride * sizeof(uint32_t)));
   CKC(cudaMalloc(&e->remaps, (size_t)e->n_slots * pn * sizeof(uint32_t)));
-  e->spill_depth = e->max_depth > (uint32_t)SMEM_LEVELS ? e->max_depth - SMEM_LEVELS : 1;
-  CKC(cudaMalloc(&e->spill_levels, (size_t)e->n_slots * e->spill_depth * sizeof(Level)));
   e->coll_len = (uint32_t)std::min<uint64_t>(pn + 1, 1u << 20);
   CKC(cudaMalloc(&e->coll_table, (size_t)e->coll_len * sizeof(uint16_t)));
   CKC(cudaMalloc(&e->d_next, sizeof(unsigned int)));
@@ -465,7 +460,6 @@ void ar_engine_destroy(ar_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaFree(e->pools); cudaFree(e->path_bufs); cudaFree(e->remaps); cudaFree(e->coll_table);
-  cudaFree(e->spill_levels);
   cudaFree(e->d_games); cudaFree(e->d_seeds); cudaFree(e->d_summaries); cudaFree(e->d_positions);
   cudaFree(e->d_search); cudaFree(e->d_next); cudaFree(e->d_counters); cudaFree(e->d_error);
   if (e->h_progress) cudaFreeHost(e->h_progress);
@@ -496,8 +490,6 @@ static RunParams make_params(ar_engine* e, const ar_search_cfg* cfg) {
   p.path_bufs = e->path_bufs;
   p.path_stride = e->path_stride;
   p.remaps = e->remaps;
-  p.spill_levels = e->spill_levels;
-  p.spill_depth = e->spill_depth;
   p.coll_table = e->coll_table;
   p.coll_table_len = e->coll_len;
   p.max_depth = e->max_depth;
