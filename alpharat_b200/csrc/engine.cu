@@ -53,13 +53,23 @@ struct RunParams {
 };
 
 __host__ __device__ inline size_t warp_smem_bytes(uint32_t max_depth, uint32_t batch_cap) {
-  size_t b = (size_t)max_depth * sizeof(Level);      // level stack
-  b += (size_t)(batch_cap + max_depth + 1) * sizeof(ChildEnt);  // per-level child lists
-  b += (size_t)batch_cap * sizeof(GState);           // leaf states
-  b += 256;                                          // maze cost table (64 cells x 4)
-  b += (size_t)batch_cap * sizeof(TpEntry);          // batch entries
+  size_t b = (size_t)batch_cap * sizeof(PendLevel);      // parked split levels
+  b += (size_t)batch_cap * sizeof(GPack);                // leaf states
+  b += (size_t)(batch_cap + 1) * sizeof(ChildEnt);       // parked (a1,a2) cells
+  b += (size_t)batch_cap * sizeof(TpEntry);              // batch entries
+  b += 256;                                              // maze cost table (64 cells x 4)
+  b += (size_t)max_depth * sizeof(uint32_t);             // current DFS path
   return (b + 15) & ~(size_t)15;
 }
+
+// Optional phase timers (-DAR_PHASE_TIMING): cycles per warp in gather / backup / advance.
+#ifdef AR_PHASE_TIMING
+#define AR_T0() long long _t0 = clock64()
+#define AR_T1(i) do { long long _t1 = clock64(); cx.phase[i] += (unsigned long long)(_t1 - _t0); _t0 = _t1; } while (0)
+#else
+#define AR_T0() do {} while (0)
+#define AR_T1(i) do {} while (0)
+#endif
 
 // One simulate_batch (search.rs:961-1073) with SmartUniformBackend fused in
 // (backend.rs:94-103: priors written when the node is created, values are 0).
@@ -69,6 +79,7 @@ __device__ __forceinline__ void simulate_batch_uniform(WarpCtx& cx, const Search
                                                        uint32_t& coll, uint32_t coll_len, int lane) {
   cx.epoch += 1;
   cx.root_claimed = false;
+  AR_T0();
   uint32_t ci = cx.node_count < coll_len ? cx.node_count : coll_len - 1;
   int collisions_left = (int)cx.coll_table[ci];
   int n_tp = 0;
@@ -79,11 +90,13 @@ __device__ __forceinline__ void simulate_batch_uniform(WarpCtx& cx, const Search
     coll += c;
   }
   if (cx.error) return;
+  AR_T1(0);
   for (int e = 0; e < n_tp; ++e) {
     uint8_t kind = cx.tp[e].kind;
     if (kind == 1) term += 1; else nn += 1;
     backup_entry(cx, e, 0.0f, 0.0f, nullptr, nullptr, lane);
   }
+  AR_T1(1);
 }
 
 __device__ __noinline__ void extract_and_store(WarpCtx& cx, const SearchParams& sp, int lane,
@@ -110,12 +123,12 @@ __device__ __forceinline__ void load_game(const ar_game_pod* pod, WarpCtx& cx, G
     reinterpret_cast<uint32_t*>(cx.maze)[i] =
         (i < cx.cells) ? reinterpret_cast<const uint32_t*>(pod->move_cost)[i] : 0u;
   g.cheese = *reinterpret_cast<const uint64_t*>(pod->cheese);
-  g.p1 = (uint8_t)(pod->p1_y * pod->width + pod->p1_x);
-  g.p2 = (uint8_t)(pod->p2_y * pod->width + pod->p2_x);
+  g.p1 = pod->p1_y * pod->width + pod->p1_x;
+  g.p2 = pod->p2_y * pod->width + pod->p2_x;
   g.mud1 = pod->p1_mud;
   g.mud2 = pod->p2_mud;
-  g.s1x2 = (uint16_t)__float2int_rn(pod->p1_score * 2.0f);
-  g.s2x2 = (uint16_t)__float2int_rn(pod->p2_score * 2.0f);
+  g.s1x2 = __float2int_rn(pod->p1_score * 2.0f);
+  g.s2x2 = __float2int_rn(pod->p2_score * 2.0f);
   __syncwarp();
 }
 
@@ -123,7 +136,10 @@ __device__ __forceinline__ void load_game(const ar_game_pod* pod, WarpCtx& cx, G
 // (game_worker_loop, selfplay.rs:609-650) and plays them to completion on device
 // (play_game, selfplay.rs:515-598).  search_only: one fresh-tree search per "game"
 // (rust_mcts_search, mcts/bindings.rs:228-304).
-__global__ void __launch_bounds__(128, 4) selfplay_uniform_kernel(RunParams p) {
+#ifndef AR_MIN_BLOCKS
+#define AR_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(RunParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -132,11 +148,12 @@ __global__ void __launch_bounds__(128, 4) selfplay_uniform_kernel(RunParams p) {
 
   uint8_t* base = smem + (size_t)wib * warp_smem_bytes(p.max_depth, p.batch_cap);
   WarpCtx cx;
-  cx.levels = reinterpret_cast<Level*>(base);
-  cx.cstack = reinterpret_cast<ChildEnt*>(base + (size_t)p.max_depth * sizeof(Level));
-  cx.tp_state = reinterpret_cast<GState*>(cx.cstack + (p.batch_cap + p.max_depth + 1));
-  cx.maze = reinterpret_cast<uint8_t*>(cx.tp_state + p.batch_cap);
-  cx.tp = reinterpret_cast<TpEntry*>(cx.maze + 256);
+  cx.pend = reinterpret_cast<PendLevel*>(base);
+  cx.tp_state = reinterpret_cast<GPack*>(cx.pend + p.batch_cap);
+  cx.cstack = reinterpret_cast<ChildEnt*>(cx.tp_state + p.batch_cap);
+  cx.tp = reinterpret_cast<TpEntry*>(cx.cstack + (p.batch_cap + 1));
+  cx.maze = reinterpret_cast<uint8_t*>(cx.tp + p.batch_cap);
+  cx.path = reinterpret_cast<uint32_t*>(cx.maze + 256);
   cx.pool = p.pools + (size_t)slot * p.pool_nodes;
   cx.path_buf = p.path_bufs + (size_t)slot * p.batch_cap * p.path_stride;
   cx.remap = p.remaps + (size_t)slot * p.pool_nodes;
@@ -150,6 +167,10 @@ __global__ void __launch_bounds__(128, 4) selfplay_uniform_kernel(RunParams p) {
   cx.error = 0;
   cx.node_count = 0;
   cx.root_claimed = false;
+#ifdef AR_PHASE_TIMING
+  for (int i = 0; i < 4; ++i) cx.phase[i] = 0;
+  long long t_begin = clock64();
+#endif
   const SearchParams sp = p.sp;
 
   for (;;) {
@@ -199,7 +220,7 @@ __global__ void __launch_bounds__(128, 4) selfplay_uniform_kernel(RunParams p) {
         ar_position_record& pr = pos[n_pos];
         pr.p1_x = (uint8_t)(g.p1 % cx.w); pr.p1_y = (uint8_t)(g.p1 / cx.w);
         pr.p2_x = (uint8_t)(g.p2 % cx.w); pr.p2_y = (uint8_t)(g.p2 / cx.w);
-        pr.p1_mud = g.mud1; pr.p2_mud = g.mud2;
+        pr.p1_mud = (uint8_t)g.mud1; pr.p2_mud = (uint8_t)g.mud2;
         pr.action_p1 = (uint8_t)a1; pr.action_p2 = (uint8_t)a2;
         pr.turn = (uint16_t)turn; pr.reserved = 0;
         pr.p1_score = 0.5f * (float)g.s1x2; pr.p2_score = 0.5f * (float)g.s2x2;
@@ -217,8 +238,10 @@ __global__ void __launch_bounds__(128, 4) selfplay_uniform_kernel(RunParams p) {
       game_step(g, a1, a2, cx.maze, cx.w);
       turn += 1;
       __syncwarp();
+      AR_T0();
       if (child != 0) {
         compact_subtree(cx, child, lane);
+        AR_T1(2);
       } else {
         cx.epoch += 1;
         init_root(cx, g, lane);  // reinit, tree.rs:298-302
@@ -239,7 +262,7 @@ __global__ void __launch_bounds__(128, 4) selfplay_uniform_kernel(RunParams p) {
       s.total_terminals = tot_term;
       s.total_collisions = tot_coll;
       // final state, consumed by the host-side cheese-outcome attribution
-      s.reserved[0] = g.p1; s.reserved[1] = g.p2; s.reserved[2] = 0;
+      s.reserved[0] = (uint8_t)g.p1; s.reserved[1] = (uint8_t)g.p2; s.reserved[2] = 0;
       *reinterpret_cast<uint64_t*>(s.cheese_outcomes) = g.cheese;
       if (p.progress) {
         atomicAdd_system((unsigned long long*)&p.progress->positions_completed, (unsigned long long)n_pos);
@@ -249,9 +272,15 @@ __global__ void __launch_bounds__(128, 4) selfplay_uniform_kernel(RunParams p) {
       }
     }
   }
+#ifdef AR_PHASE_TIMING
+  cx.phase[3] = (unsigned long long)(clock64() - t_begin);
+#endif
   if (lane == 0) {
     atomicAdd(&p.counters[0], (unsigned long long)cx.path_nodes);
     atomicAdd(&p.counters[1], (unsigned long long)cx.new_nodes);
+#ifdef AR_PHASE_TIMING
+    for (int i = 0; i < 4; ++i) atomicAdd(&p.counters[2 + i], cx.phase[i]);
+#endif
     if (cx.error) atomicCAS(p.error_flag, 0, (int)cx.error);
   }
 }
@@ -630,6 +659,9 @@ static ar_status run_resident(ar_engine* e, const ar_search_cfg* cfg, ar_progres
     stats->path_nodes = c[0];
     stats->new_nodes = c[1];
     stats->kernel_launches = n > 0 ? 1 : 0;
+#ifdef AR_PHASE_TIMING
+    fprintf(stderr, "[phase cycles] gather=%llu backup=%llu advance=%llu total=%llu\n", c[2], c[3], c[4], c[5]);
+#endif
   }
   return AR_OK;
 }

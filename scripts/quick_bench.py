@@ -8,7 +8,7 @@ pods = pods_array(specs)
 cfg = search_cfg(simulations=1897, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103)
 eng = Engine(concurrent_games=conc, max_turns=50, max_batch_size=16, max_simulations=1897)
 eng.selfplay_upload(pods, list(range(n)))
-for it in range(2):
+for it in range(int(sys.argv[3]) if len(sys.argv)>3 else 2):
     st = eng.selfplay_run_resident(cfg)
     summ, pos = eng.selfplay_download(n, 50)
     npos = sum(summ[i].n_positions for i in range(n))
