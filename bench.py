@@ -6,7 +6,7 @@
 Workload (BASELINE.json configs[1]): PyRat 7x7 open maze, 10 cheese, 50 turns, `7x7_rust_tuned`
 (1897 sims, c_puct 0.512, fpu 0.459, force_k 0.103, batch 16), uniform priors, Dirichlet noise 0,
 4096 concurrent game trees per GPU.  One step = one pass of the hot path over one batch of
-synthetic games (`--games-per-step` per GPU, default 16384, played to completion through the
+synthetic games (`--games-per-step` per GPU, default 65536, played to completion through the
 4096 resident trees; fresh games every step).
 
 Metric: self-play MCTS simulations/sec, counted as S_new = descents performed
@@ -304,7 +304,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--games-per-step", type=int, default=16384)
+    ap.add_argument("--games-per-step", type=int, default=65536)
     ap.add_argument("--concurrent", type=int, default=4096)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

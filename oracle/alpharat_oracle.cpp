@@ -114,14 +114,16 @@ GameState GameState::from_pod(const ar_game_pod& p) {
   g.p1x = p.p1_x; g.p1y = p.p1_y; g.p2x = p.p2_x; g.p2y = p.p2_y;
   g.mud1 = p.p1_mud; g.mud2 = p.p2_mud;
   g.s1 = p.p1_score; g.s2 = p.p2_score;
-  std::memcpy(g.move_cost, p.move_cost, sizeof(g.move_cost));
+  auto m = std::make_shared<MazeData>();
+  std::memcpy(m->move_cost, p.move_cost, sizeof(m->move_cost));
+  g.maze = m;
   g.remaining = 0;
   int cells = (int)p.width * p.height;
-  for (int c = 0; c < AR_MAX_CELLS; ++c) {
-    bool has = c < cells && ((p.cheese[c >> 3] >> (c & 7)) & 1);
-    g.cheese[c] = has ? 1 : 0;
-    g.remaining += has ? 1 : 0;
-  }
+  for (int c = 0; c < cells; ++c)
+    if ((p.cheese[c >> 3] >> (c & 7)) & 1) {
+      g.set_cheese(c, true);
+      g.remaining++;
+    }
   return g;
 }
 
@@ -130,9 +132,9 @@ void GameState::to_pod(ar_game_pod& p) const {
   p.width = width; p.height = height; p.turn = turn; p.max_turns = max_turns;
   p.p1_x = p1x; p.p1_y = p1y; p.p2_x = p2x; p.p2_y = p2y;
   p.p1_mud = mud1; p.p2_mud = mud2; p.p1_score = s1; p.p2_score = s2;
-  std::memcpy(p.move_cost, move_cost, sizeof(move_cost));
+  std::memcpy(p.move_cost, maze->move_cost, sizeof(maze->move_cost));
   for (int c = 0; c < AR_MAX_CELLS; ++c)
-    if (cheese[c]) p.cheese[c >> 3] |= (uint8_t)(1u << (c & 7));
+    if (has_cheese(c)) p.cheese[c >> 3] |= (uint8_t)(1u << (c & 7));
 }
 
 void GameState::effective_actions(int x, int y, uint8_t mud, uint8_t out[5]) const {
@@ -141,7 +143,7 @@ void GameState::effective_actions(int x, int y, uint8_t mud, uint8_t out[5]) con
   if (mud > 0) return;
   int c = cell(x, y);
   for (int a = 0; a < 4; ++a)
-    if (move_cost[c * 4 + a] != 0) out[a] = (uint8_t)a;
+    if (cost(c, a) != 0) out[a] = (uint8_t)a;
 }
 
 static void step_player(const GameState& g, uint8_t& x, uint8_t& y, uint8_t& mud, uint8_t d) {
@@ -150,7 +152,7 @@ static void step_player(const GameState& g, uint8_t& x, uint8_t& y, uint8_t& mud
     return;
   }
   if (d >= 4) return;
-  uint8_t cost = g.move_cost[g.cell(x, y) * 4 + d];
+  uint8_t cost = g.cost(g.cell(x, y), d);
   if (cost == 0) return;  // wall / boundary: a blocked move is a stay
   x = (uint8_t)(x + DX[d]);
   y = (uint8_t)(y + DY[d]);
@@ -167,19 +169,19 @@ MoveUndo GameState::make_move(uint8_t d1, uint8_t d2) {
   bool c1 = mud1 == 0, c2 = mud2 == 0;
   int k1 = cell(p1x, p1y), k2 = cell(p2x, p2y);
   if (c1 && c2 && k1 == k2) {
-    if (cheese[k1]) {
-      cheese[k1] = 0; remaining--;
+    if (has_cheese(k1)) {
+      set_cheese(k1, false); remaining--;
       s1 += 0.5f; s2 += 0.5f;
       u.collected[u.n_collected++] = (uint16_t)k1;
     }
   } else {
-    if (c1 && cheese[k1]) {
-      cheese[k1] = 0; remaining--;
+    if (c1 && has_cheese(k1)) {
+      set_cheese(k1, false); remaining--;
       s1 += 1.0f;
       u.collected[u.n_collected++] = (uint16_t)k1;
     }
-    if (c2 && cheese[k2]) {
-      cheese[k2] = 0; remaining--;
+    if (c2 && has_cheese(k2)) {
+      set_cheese(k2, false); remaining--;
       s2 += 1.0f;
       u.collected[u.n_collected++] = (uint16_t)k2;
     }
@@ -192,7 +194,7 @@ void GameState::unmake_move(const MoveUndo& u) {
   p1x = u.p1x; p1y = u.p1y; p2x = u.p2x; p2y = u.p2y; mud1 = u.mud1; mud2 = u.mud2;
   s1 = u.s1; s2 = u.s2; turn = u.turn;
   for (int i = 0; i < u.n_collected; ++i) {
-    cheese[u.collected[i]] = 1;
+    set_cheese(u.collected[i], true);
     remaining++;
   }
 }
@@ -1018,7 +1020,7 @@ static void cheese_bits(const GameState& g, uint8_t out[AR_MAX_CELLS / 8]) {
   std::memset(out, 0, AR_MAX_CELLS / 8);
   int cells = g.width * g.height;
   for (int c = 0; c < cells; ++c)
-    if (g.cheese[c]) out[c >> 3] |= (uint8_t)(1u << (c & 7));
+    if (g.has_cheese(c)) out[c >> 3] |= (uint8_t)(1u << (c & 7));
 }
 
 static void fill_search_result(ar_search_result& o, const SearchResult& r, const MCTSTree& tree) {
@@ -1121,14 +1123,14 @@ void encode_flat(const GameState& g, float* out) {
   for (int i = 0; i < spatial * 4; ++i) out[i] = -1.0f;
   for (int c = 0; c < spatial; ++c)
     for (int d = 0; d < 4; ++d) {
-      uint8_t cost = g.move_cost[c * 4 + d];
+      uint8_t cost = g.cost(c, d);
       if (cost == 0) continue;
       out[c * 4 + d] = cost >= 2 ? (float)cost / MAX_MUD_COST : 1.0f / MAX_MUD_COST;
     }
   for (int j = 0; j < spatial * 3; ++j) out[spatial * 4 + j] = 0.0f;
   out[spatial * 4 + g.cell(g.p1x, g.p1y)] = 1.0f;
   out[spatial * 5 + g.cell(g.p2x, g.p2y)] = 1.0f;
-  for (int c = 0; c < spatial; ++c) out[spatial * 6 + c] = g.cheese[c] ? 1.0f : 0.0f;
+  for (int c = 0; c < spatial; ++c) out[spatial * 6 + c] = g.has_cheese(c) ? 1.0f : 0.0f;
   float* s = out + spatial * 7;
   s[0] = g.s1 - g.s2;
   s[1] = g.max_turns > 0 ? (float)g.turn / (float)g.max_turns : 0.0f;

@@ -28,6 +28,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "../include/alpharat_cuda.h"
@@ -67,18 +68,27 @@ struct MoveUndo {
   uint16_t collected[2];
 };
 
+struct MazeData {  // immutable per game: shared by every clone of the state (cheap clone())
+  uint8_t move_cost[AR_MAX_CELLS * 4];
+};
+
 struct GameState {
   uint8_t width = 0, height = 0;
   uint16_t turn = 0, max_turns = 0;
   uint8_t p1x = 0, p1y = 0, p2x = 0, p2y = 0, mud1 = 0, mud2 = 0;
   float s1 = 0.f, s2 = 0.f;
-  uint8_t move_cost[AR_MAX_CELLS * 4];
-  uint8_t cheese[AR_MAX_CELLS];
+  std::shared_ptr<MazeData> maze;
+  uint64_t cheese_bits[AR_MAX_CELLS / 64] = {0, 0, 0, 0};
   uint16_t remaining = 0;
 
   static GameState from_pod(const ar_game_pod& p);
   void to_pod(ar_game_pod& p) const;
   int cell(int x, int y) const { return y * width + x; }
+  uint8_t cost(int c, int d) const { return maze->move_cost[c * 4 + d]; }
+  bool has_cheese(int c) const { return (cheese_bits[c >> 6] >> (c & 63)) & 1; }
+  void set_cheese(int c, bool v) {
+    if (v) cheese_bits[c >> 6] |= 1ULL << (c & 63); else cheese_bits[c >> 6] &= ~(1ULL << (c & 63));
+  }
   void effective_actions(int x, int y, uint8_t mud, uint8_t out[5]) const;
   void effective_actions_p1(uint8_t out[5]) const { effective_actions(p1x, p1y, mud1, out); }
   void effective_actions_p2(uint8_t out[5]) const { effective_actions(p2x, p2y, mud2, out); }

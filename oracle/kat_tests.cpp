@@ -47,26 +47,26 @@ static GameState open_game(int w, int h, int p1x, int p1y, int p2x, int p2y,
   GameState g;
   g.width = (uint8_t)w; g.height = (uint8_t)h; g.max_turns = (uint16_t)max_turns;
   g.p1x = (uint8_t)p1x; g.p1y = (uint8_t)p1y; g.p2x = (uint8_t)p2x; g.p2y = (uint8_t)p2y;
-  std::memset(g.move_cost, 0, sizeof(g.move_cost));
-  std::memset(g.cheese, 0, sizeof(g.cheese));
+  g.maze = std::make_shared<MazeData>();
+  std::memset(g.maze->move_cost, 0, sizeof(g.maze->move_cost));
   for (int y = 0; y < h; ++y)
     for (int x = 0; x < w; ++x) {
       int c = y * w + x;
-      g.move_cost[c * 4 + 0] = y + 1 < h;
-      g.move_cost[c * 4 + 1] = x + 1 < w;
-      g.move_cost[c * 4 + 2] = y > 0;
-      g.move_cost[c * 4 + 3] = x > 0;
+      g.maze->move_cost[c * 4 + 0] = y + 1 < h;
+      g.maze->move_cost[c * 4 + 1] = x + 1 < w;
+      g.maze->move_cost[c * 4 + 2] = y > 0;
+      g.maze->move_cost[c * 4 + 3] = x > 0;
     }
   for (auto& c : cheese) {
-    g.cheese[c.second * w + c.first] = 1;
+    g.set_cheese(c.second * w + c.first, true);
     g.remaining++;
   }
   return g;
 }
 static void add_wall(GameState& g, int x1, int y1, int x2, int y2, uint8_t val = 0) {
   int d = (x2 == x1) ? (y2 > y1 ? 0 : 2) : (x2 > x1 ? 1 : 3);
-  g.move_cost[(y1 * g.width + x1) * 4 + d] = val;
-  g.move_cost[(y2 * g.width + x2) * 4 + ((d + 2) % 4)] = val;
+  g.maze->move_cost[(y1 * g.width + x1) * 4 + d] = val;
+  g.maze->move_cost[(y2 * g.width + x2) * 4 + ((d + 2) % 4)] = val;
 }
 
 int main() {
