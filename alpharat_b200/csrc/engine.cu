@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "mcts_device.cuh"
+#include "nn_api.cuh"
 
 namespace ar {
 
@@ -322,6 +323,13 @@ struct ar_engine {
   ar_progress* h_progress = nullptr;  // mapped pinned
   ar_progress* d_progress = nullptr;
   uint64_t h2d = 0, d2h = 0, launches = 0;
+  // leaf evaluator
+  int arch = AR_ARCH_UNIFORM;
+  int nn_width = 0, nn_height = 0;
+  MlpModel mlp;
+  EvalRow* d_rows = nullptr;
+  float* d_nn_out = nullptr;
+  int cap_rows = 0;
 };
 
 static thread_local std::string g_create_error;
@@ -417,6 +425,45 @@ static ar_status validate_games(ar_engine* e, const ar_game_pod* games, int n) {
   return AR_OK;
 }
 
+static void pod_to_row(const ar_game_pod& g, uint32_t game_idx, EvalRow& r) {
+  memset(&r, 0, sizeof(r));
+  memcpy(&r.cheese, g.cheese, 8);
+  uint32_t p1 = (uint32_t)g.p1_y * g.width + g.p1_x, p2 = (uint32_t)g.p2_y * g.width + g.p2_x;
+  r.pos = p1 | (p2 << 8) | ((uint32_t)g.p1_mud << 16) | ((uint32_t)g.p2_mud << 24);
+  r.score = (uint32_t)lrintf(g.p1_score * 2.0f) | ((uint32_t)lrintf(g.p2_score * 2.0f) << 16);
+  r.game_idx = game_idx;
+  r.turn = g.turn;
+  r.max_turns = g.max_turns;
+}
+
+// Stage n positions as evaluator rows (each row points at its own pod for the maze).
+static ar_status stage_rows(ar_engine* e, const ar_game_pod* games, int n) {
+  ar_status s = validate_games(e, games, n);
+  if (s) return s;
+  if (n > e->cap_games) {
+    cudaFree(e->d_games); cudaFree(e->d_seeds); cudaFree(e->d_summaries); cudaFree(e->d_positions);
+    e->d_games = nullptr; e->d_seeds = nullptr; e->d_summaries = nullptr; e->d_positions = nullptr;
+    CK(cudaMalloc(&e->d_games, (size_t)n * sizeof(ar_game_pod)));
+    CK(cudaMalloc(&e->d_seeds, (size_t)n * sizeof(uint64_t)));
+    CK(cudaMalloc(&e->d_summaries, (size_t)n * sizeof(ar_game_summary)));
+    e->cap_games = n;
+    e->cap_stride = 0;
+  }
+  if (n > e->cap_rows) {
+    cudaFree(e->d_rows); cudaFree(e->d_nn_out);
+    e->d_rows = nullptr; e->d_nn_out = nullptr;
+    CK(cudaMalloc(&e->d_rows, (size_t)n * sizeof(EvalRow)));
+    CK(cudaMalloc(&e->d_nn_out, (size_t)n * 12 * sizeof(float)));
+    e->cap_rows = n;
+  }
+  std::vector<EvalRow> rows(n);
+  for (int i = 0; i < n; ++i) pod_to_row(games[i], (uint32_t)i, rows[i]);
+  CK(cudaMemcpyAsync(e->d_games, games, (size_t)n * sizeof(ar_game_pod), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->d_rows, rows.data(), (size_t)n * sizeof(EvalRow), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return AR_OK;
+}
+
 extern "C" {
 
 uint32_t ar_abi_version(void) { return AR_ABI_VERSION; }
@@ -491,6 +538,8 @@ void ar_engine_destroy(ar_engine* e) {
   cudaFree(e->pools); cudaFree(e->path_bufs); cudaFree(e->remaps); cudaFree(e->coll_table);
   cudaFree(e->d_games); cudaFree(e->d_seeds); cudaFree(e->d_summaries); cudaFree(e->d_positions);
   cudaFree(e->d_search); cudaFree(e->d_next); cudaFree(e->d_counters); cudaFree(e->d_error);
+  cudaFree(e->d_rows); cudaFree(e->d_nn_out);
+  e->mlp.release();
   if (e->h_progress) cudaFreeHost(e->h_progress);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
@@ -498,11 +547,27 @@ void ar_engine_destroy(ar_engine* e) {
   delete e;
 }
 
-ar_status ar_engine_load_weights(ar_engine* e, int32_t arch, int32_t, int32_t, const ar_tensor_desc*, int32_t) {
+ar_status ar_engine_load_weights(ar_engine* e, int32_t arch, int32_t width, int32_t height,
+                                 const ar_tensor_desc* tensors, int32_t n_tensors) {
   if (!e) return AR_ERR_INVALID_ARG;
-  if (arch == AR_ARCH_UNIFORM) return AR_OK;
-  e->err = "NN evaluators are not built into this library yet";
-  return AR_ERR_UNSUPPORTED;
+  CK(cudaSetDevice(e->device));
+  if (arch == AR_ARCH_UNIFORM) {
+    e->mlp.release();
+    e->arch = AR_ARCH_UNIFORM;
+    return AR_OK;
+  }
+  if (arch != AR_ARCH_MLP) {
+    e->err = "architecture " + std::to_string(arch) + " has no CUDA evaluator in this build (MLP only)";
+    return AR_ERR_UNSUPPORTED;
+  }
+  if (width <= 0 || height <= 0 || width * height > 64) { e->err = "bad board size"; return AR_ERR_INVALID_ARG; }
+  if (!tensors || n_tensors <= 0) { e->err = "no tensors"; return AR_ERR_INVALID_ARG; }
+  int rc = e->mlp.load(tensors, n_tensors, width, height, e->err);
+  if (rc != AR_OK) return (ar_status)rc;
+  e->arch = arch;
+  e->nn_width = width;
+  e->nn_height = height;
+  return AR_OK;
 }
 
 static RunParams make_params(ar_engine* e, const ar_search_cfg* cfg) {
@@ -767,16 +832,58 @@ ar_status ar_selfplay_run(ar_engine* e, const ar_game_pod* games, int32_t n, con
   return AR_OK;
 }
 
-ar_status ar_encode_observations(ar_engine* e, const ar_game_pod*, int32_t, float*) {
+ar_status ar_encode_observations(ar_engine* e, const ar_game_pod* games, int32_t n, float* obs) {
   if (!e) return AR_ERR_INVALID_ARG;
-  e->err = "ar_encode_observations: NN path not built yet";
-  return AR_ERR_UNSUPPORTED;
+  CK(cudaSetDevice(e->device));
+  if (n == 0) return AR_OK;
+  if (!obs) { e->err = "obs is NULL"; return AR_ERR_INVALID_ARG; }
+  ar_status s = stage_rows(e, games, n);
+  if (s) return s;
+  int dim = 7 * games[0].width * games[0].height + 6;
+  for (int i = 1; i < n; ++i)
+    if (games[i].width != games[0].width || games[i].height != games[0].height) {
+      e->err = "all games of one call must share the board size";
+      return AR_ERR_INVALID_ARG;
+    }
+  float* d_obs = nullptr;
+  CK(cudaMalloc(&d_obs, (size_t)n * dim * sizeof(float)));
+  cudaError_t ce = encode_f32(e->d_rows, n, e->d_games, dim, d_obs, e->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(obs, d_obs, (size_t)n * dim * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  cudaFree(d_obs);
+  if (ce != cudaSuccess) { e->err = std::string("encode: ") + cudaGetErrorString(ce); return AR_ERR_CUDA; }
+  return AR_OK;
 }
 
-ar_status ar_nn_forward(ar_engine* e, const ar_game_pod*, int32_t, float*, float*, float*, float*) {
+ar_status ar_nn_forward(ar_engine* e, const ar_game_pod* games, int32_t n, float* policy_p1, float* policy_p2,
+                        float* value_p1, float* value_p2) {
   if (!e) return AR_ERR_INVALID_ARG;
-  e->err = "ar_nn_forward: NN path not built yet";
-  return AR_ERR_UNSUPPORTED;
+  CK(cudaSetDevice(e->device));
+  if (e->arch == AR_ARCH_UNIFORM || !e->mlp.loaded) { e->err = "no evaluator loaded (ar_engine_load_weights)"; return AR_ERR_NO_WEIGHTS; }
+  if (n == 0) return AR_OK;
+  if (!policy_p1 || !policy_p2 || !value_p1 || !value_p2) { e->err = "output is NULL"; return AR_ERR_INVALID_ARG; }
+  ar_status s = stage_rows(e, games, n);
+  if (s) return s;
+  for (int i = 0; i < n; ++i)
+    if (games[i].width != e->nn_width || games[i].height != e->nn_height) {
+      e->err = "game " + std::to_string(i) + " does not match the evaluator's board size";
+      return AR_ERR_INVALID_ARG;
+    }
+  CK(cudaMemsetAsync(e->d_error, 0, sizeof(int), e->stream));
+  CK(e->mlp.forward(e->d_rows, nullptr, n, e->d_games, e->d_nn_out, e->d_error, e->stream));
+  std::vector<float> out((size_t)n * 12);
+  CK(cudaMemcpyAsync(out.data(), e->d_nn_out, out.size() * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  int herr = 0;
+  CK(cudaMemcpyAsync(&herr, e->d_error, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  if (herr) { e->err = "evaluator produced a non-finite value"; return (ar_status)herr; }
+  for (int i = 0; i < n; ++i) {
+    memcpy(policy_p1 + i * 5, &out[(size_t)i * 12], 20);
+    memcpy(policy_p2 + i * 5, &out[(size_t)i * 12 + 5], 20);
+    value_p1[i] = out[(size_t)i * 12 + 10];
+    value_p2[i] = out[(size_t)i * 12 + 11];
+  }
+  return AR_OK;
 }
 
 }  // extern "C"

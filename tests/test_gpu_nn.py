@@ -1,0 +1,83 @@
+"""GPU leaf evaluator (on-device encode + tcgen05 MLP) against golden vectors of the real reference.
+
+Tolerances (stated, bf16 operands with fp32 accumulation):
+  vs reference torch fp32 (tests/golden/mlp_7x7.npz):  |d policy| <= 2e-2,  |d value| <= 3e-2 * max(1, |v|)
+  vs the bf16-emulating restatement (tests/nn_ref.py):  |d policy| <= 2e-3,  |d value| <= 4e-3 * max(1, |v|)
+Observation encoding is exact f32 work: <= 1e-6 like the reference's own parity test (parity.rs:16).
+"""
+
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from alpharat_b200 import _native as N
+from alpharat_b200.engine import Engine
+from alpharat_b200.games import GameSpec, pods_array
+from nn_ref import make_mlp_state_dict, mlp_forward, random_positions
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def test_encode_matches_reference_builder():
+    specs = random_positions(96, 7, 7, seed=123)
+    gold = np.load(GOLD / "flat_builder_7x7.npz")["obs"]
+    with Engine(concurrent_games=4, max_turns=120) as eng:
+        obs = eng.encode(pods_array(specs))
+    assert obs.shape == gold.shape == (96, 349)
+    assert np.abs(obs - gold).max() <= 1e-6
+
+
+def test_encode_matches_rust_fixtures(oracle):
+    """The 7 JSON fixtures of crates/alpharat-sampling/tests/parity.rs (moves replayed by the oracle)."""
+    fx = json.loads((GOLD / "encoder_fixtures.json").read_text())
+    with Engine(concurrent_games=4, max_turns=120) as eng:
+        for f in fx:
+            spec = GameSpec(f["width"], f["height"], f["max_turns"], tuple(f["p1"]), tuple(f["p2"]),
+                            [tuple(c) for c in f["cheese"]],
+                            walls=[(tuple(a), tuple(b)) for a, b in f["walls"]],
+                            mud=[(tuple(a), tuple(b), v) for a, b, v in f["mud"]])
+            pods = pods_array([spec])
+            for d1, d2 in f["moves"]:
+                oracle.orc_game_make_move(pods, d1, d2)
+            obs = eng.encode(pods)[0]
+            exp = np.asarray(f["expected"], dtype=np.float32)
+            assert obs.shape == exp.shape, f["name"]
+            assert np.abs(obs - exp).max() <= 1e-6, f["name"]
+
+
+@pytest.mark.parametrize("n", [1, 96, 128, 129, 1000])
+def test_mlp_forward_matches_reference(n):
+    base = random_positions(96, 7, 7, seed=123)
+    specs = [base[i % 96] for i in range(n)]
+    sd = make_mlp_state_dict(0, 349)
+    gold = np.load(GOLD / "mlp_7x7.npz")
+    obs = np.load(GOLD / "flat_builder_7x7.npz")["obs"]
+    with Engine(concurrent_games=4, max_turns=120) as eng:
+        eng.load_weights(N.AR_ARCH_MLP, 7, 7, sd)
+        p1, p2, v1, v2 = eng.nn_forward(pods_array(specs))
+    idx = np.arange(n) % 96
+    # reference torch fp32
+    assert np.abs(p1 - gold["policy_p1"][idx]).max() <= 2e-2
+    assert np.abs(p2 - gold["policy_p2"][idx]).max() <= 2e-2
+    for v, g in ((v1, gold["value_p1"][idx]), (v2, gold["value_p2"][idx])):
+        assert (np.abs(v - g) <= 3e-2 * np.maximum(1.0, np.abs(g))).all()
+    # bf16-emulating restatement: isolates layout bugs from precision
+    e1, e2, ev1, ev2 = mlp_forward(sd, obs[idx], emulate_bf16=True)
+    assert np.abs(p1 - e1).max() <= 2e-3
+    assert np.abs(p2 - e2).max() <= 2e-3
+    for v, g in ((v1, ev1), (v2, ev2)):
+        assert (np.abs(v - g) <= 4e-3 * np.maximum(1.0, np.abs(g))).all()
+    assert np.allclose(p1.sum(1), 1, atol=1e-5) and np.allclose(p2.sum(1), 1, atol=1e-5)
+    assert (v1 >= 0).all() and (v2 >= 0).all()
+
+
+def test_nn_forward_without_weights_fails_loudly():
+    specs = random_positions(2, 7, 7, seed=1)
+    with Engine(concurrent_games=4, max_turns=120) as eng:
+        with pytest.raises(RuntimeError, match="no evaluator"):
+            eng.nn_forward(pods_array(specs))
