@@ -286,6 +286,292 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(Ru
   }
 }
 
+
+// =========================================================================================
+// NN-guided mode: the search is cut at the evaluator.  One step = tree kernel (back up the
+// previous batch with the evaluator's outputs, finish moves / games, gather the next batch and
+// append its leaves to the global evaluation queue) followed by the fused encode+MLP kernel
+// over the queue (nn_kernels.cu).  The host only enqueues steps; it reads one counter every few
+// steps to know when every game is finished.  Replaces MuxBackend's cross-game batching
+// (crates/alpharat-sampling/src/backends/mux.rs:170-289).
+// =========================================================================================
+enum SlotPhase : uint32_t { PH_IDLE = 0, PH_GATHER = 1, PH_WAIT_EVAL = 2, PH_DONE = 3 };
+
+struct SlotState {
+  GPack g;
+  Rng rng;
+  unsigned long long tot_sims, tot_nn, tot_term, tot_coll;
+  int turn, gi;
+  uint32_t node_count, epoch;
+  uint32_t remaining, nn, term, coll;
+  uint32_t n_pos, cheese_available;
+  uint32_t n_tp, row_base;
+  uint32_t phase, error;
+  uint32_t path_nodes, new_nodes;
+  uint32_t pad[2];
+};
+
+struct NnParams {
+  SlotState* slots;
+  TpEntry* tp_store;        // [n_slots][batch_cap]
+  EvalRow* rows;            // evaluation queue
+  uint32_t* n_rows;         // queue length (reset by the host every step)
+  const float* nn_out;      // [rows][12] from the previous step
+  uint32_t* done_slots;
+  uint32_t max_rows;
+};
+
+__global__ void nn_init_slots_kernel(SlotState* slots, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  SlotState st;
+  memset(&st, 0, sizeof(st));
+  st.phase = PH_IDLE;
+  st.gi = -1;
+  st.epoch = 1;
+  slots[i] = st;
+}
+
+__global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p, NnParams q) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int slot = blockIdx.x * 4 + wib;
+  if (slot >= p.n_slots) return;
+  SlotState* sp_g = q.slots + slot;
+  if (sp_g->phase == PH_DONE) return;
+
+  uint8_t* base = smem + (size_t)wib * warp_smem_bytes(p.max_depth, p.batch_cap);
+  WarpCtx cx;
+  cx.pend = reinterpret_cast<PendLevel*>(base);
+  cx.tp_state = reinterpret_cast<GPack*>(cx.pend + p.batch_cap);
+  cx.cstack = reinterpret_cast<ChildEnt*>(cx.tp_state + p.batch_cap);
+  cx.tp = reinterpret_cast<TpEntry*>(cx.cstack + (p.batch_cap + 1));
+  cx.maze = reinterpret_cast<uint8_t*>(cx.tp + p.batch_cap);
+  cx.path = reinterpret_cast<uint32_t*>(cx.maze + 256);
+  cx.pool = p.pools + (size_t)slot * p.pool_nodes;
+  cx.path_buf = p.path_bufs + (size_t)slot * p.batch_cap * p.path_stride;
+  cx.remap = p.remaps + (size_t)slot * p.pool_nodes;
+  cx.coll_table = p.coll_table;
+  cx.pool_nodes = p.pool_nodes;
+  cx.path_stride = p.path_stride;
+  cx.max_depth = p.max_depth;
+  const SearchParams sp = p.sp;
+
+  SlotState st = *sp_g;
+  cx.epoch = st.epoch;
+  cx.node_count = st.node_count;
+  cx.path_nodes = st.path_nodes;
+  cx.new_nodes = st.new_nodes;
+  cx.error = st.error;
+  cx.root_claimed = false;
+  GState g = g_unpack(st.g);
+  Rng rng = st.rng;
+  int turn = st.turn;
+  if (st.gi >= 0) {
+    int dummy_turn;
+    GState dummy;
+    load_game(p.games + st.gi, cx, dummy, dummy_turn, lane);  // maze + board constants
+  }
+  TpEntry* tp_g = q.tp_store + (size_t)slot * p.batch_cap;
+
+  for (int iter = 0; iter < 6 && cx.error == 0; ++iter) {
+    if (st.phase == PH_IDLE) {
+      unsigned int gi = 0;
+      if (lane == 0) gi = atomicAdd(p.next_game, 1u);
+      gi = __shfl_sync(FULL, gi, 0);
+      if (gi >= (unsigned)p.n_games) {
+        st.phase = PH_DONE;
+        st.gi = -1;
+        if (lane == 0) atomicAdd(q.done_slots, 1u);
+        break;
+      }
+      st.gi = (int)gi;
+      load_game(p.games + gi, cx, g, turn, lane);
+      rng = rng_seed(p.seeds[gi]);
+      st.cheese_available = __popcll(g.cheese);
+      cx.epoch += 1;
+      init_root(cx, g, lane);
+      st.n_pos = 0;
+      st.tot_sims = st.tot_nn = st.tot_term = st.tot_coll = 0;
+      st.remaining = sp.n_sims;
+      st.nn = st.term = st.coll = 0;
+      st.phase = PH_GATHER;
+      if (!p.search_only && game_over(g, turn, cx.max_turns)) st.remaining = 0;  // empty game
+    }
+    if (st.phase == PH_WAIT_EVAL) {
+      // ---- populate + backup in to_process order (search.rs:1028-1058)
+      const int n_tp = (int)st.n_tp;
+      for (int e = lane; e < n_tp; e += 32) cx.tp[e] = tp_g[e];
+      __syncwarp();
+      uint32_t row = st.row_base, nn_b = 0, term_b = 0;
+      for (int e = 0; e < n_tp; ++e) {
+        if (cx.tp[e].kind == 0) {
+          const float* o = q.nn_out + (size_t)row * 12;
+          row += 1;
+          nn_b += 1;
+          backup_entry(cx, e, o[10], o[11], o, o + 5, lane);
+        } else {
+          term_b += 1;
+          backup_entry(cx, e, 0.0f, 0.0f, nullptr, nullptr, lane);
+        }
+      }
+      st.nn += nn_b;
+      st.term += term_b;
+      uint32_t produced = nn_b + term_b;
+      produced = produced > 1u ? produced : 1u;
+      st.remaining = st.remaining > produced ? st.remaining - produced : 0u;
+      st.phase = PH_GATHER;
+    }
+    if (st.phase == PH_GATHER) {
+      if (st.remaining == 0) {
+        // ---- search finished: extract_result, then one self-play move (selfplay.rs:547-565)
+        const bool empty_game = !p.search_only && game_over(g, turn, cx.max_turns);
+        if (!empty_game) {
+          float pol1[5], pol2[5];
+          ar_position_record* pos = p.positions ? p.positions + (size_t)st.gi * p.pos_stride : nullptr;
+          ar_search_result* rout = p.search_only ? (p.search_out + st.gi) : &pos[st.n_pos].search;
+          extract_and_store(cx, sp, lane, rout, st.nn, st.term, st.coll, pol1, pol2);
+          if (p.search_only) {
+            st.phase = PH_IDLE;
+            continue;
+          }
+          uint32_t tv = 0;
+          if (lane == 0) tv = rout->total_visits;
+          tv = __shfl_sync(FULL, tv, 0);
+          st.tot_sims += tv; st.tot_nn += st.nn; st.tot_term += st.term; st.tot_coll += st.coll;
+          int a1 = rng_sample_action(rng, pol1);
+          int a2 = rng_sample_action(rng, pol2);
+          if (lane == 0) {
+            ar_position_record& pr = pos[st.n_pos];
+            pr.p1_x = (uint8_t)(g.p1 % cx.w); pr.p1_y = (uint8_t)(g.p1 / cx.w);
+            pr.p2_x = (uint8_t)(g.p2 % cx.w); pr.p2_y = (uint8_t)(g.p2 / cx.w);
+            pr.p1_mud = (uint8_t)g.mud1; pr.p2_mud = (uint8_t)g.mud2;
+            pr.action_p1 = (uint8_t)a1; pr.action_p2 = (uint8_t)a2;
+            pr.turn = (uint16_t)turn; pr.reserved = 0;
+            pr.p1_score = 0.5f * (float)g.s1x2; pr.p2_score = 0.5f * (float)g.s2x2;
+            uint32_t* cb = reinterpret_cast<uint32_t*>(pr.cheese);
+            cb[0] = (uint32_t)g.cheese; cb[1] = (uint32_t)(g.cheese >> 32);
+#pragma unroll
+            for (int t = 2; t < 8; ++t) cb[t] = 0;
+          }
+          st.n_pos += 1;
+          uint32_t rmeta = cx.pool[0].s[LANE_LINKS].y;
+          int i = action_to_idx(meta_m1(rmeta), a1), j = action_to_idx(meta_m2(rmeta), a2);
+          uint32_t child = reinterpret_cast<const uint32_t*>(&cx.pool[0].s[LANE_CHILD])[i * 5 + j];
+          game_step(g, a1, a2, cx.maze, cx.w);
+          turn += 1;
+          __syncwarp();
+          if (child != 0) {
+            compact_subtree(cx, child, lane);
+          } else {
+            cx.epoch += 1;
+            init_root(cx, g, lane);
+          }
+        }
+        if (game_over(g, turn, cx.max_turns)) {
+          if (lane == 0) {
+            ar_game_summary& s = p.summaries[st.gi];
+            s.game_index = (uint32_t)st.gi;
+            s.n_positions = st.n_pos;
+            s.final_p1_score = 0.5f * (float)g.s1x2;
+            s.final_p2_score = 0.5f * (float)g.s2x2;
+            s.result = g.s1x2 > g.s2x2 ? 1 : (g.s2x2 > g.s1x2 ? 2 : 0);
+            s.cheese_available = (uint16_t)st.cheese_available;
+            s.total_simulations = st.tot_sims;
+            s.total_nn_evals = st.tot_nn;
+            s.total_terminals = st.tot_term;
+            s.total_collisions = st.tot_coll;
+            s.reserved[0] = (uint8_t)g.p1; s.reserved[1] = (uint8_t)g.p2; s.reserved[2] = 0;
+            *reinterpret_cast<uint64_t*>(s.cheese_outcomes) = g.cheese;
+            if (p.progress) {
+              atomicAdd_system((unsigned long long*)&p.progress->positions_completed, (unsigned long long)st.n_pos);
+              atomicAdd_system((unsigned long long*)&p.progress->simulations_completed, st.tot_sims);
+              atomicAdd_system((unsigned long long*)&p.progress->nn_evals_completed, st.tot_nn);
+              atomicAdd_system((unsigned int*)&p.progress->games_completed, 1u);
+            }
+          }
+          st.phase = PH_IDLE;
+          continue;
+        }
+        st.remaining = sp.n_sims;
+        st.nn = st.term = st.coll = 0;
+      }
+      // ---- gather one batch (simulate_batch up to the evaluator, search.rs:961-1023)
+      cx.epoch += 1;
+      cx.root_claimed = false;
+      const uint32_t bs = min(st.remaining, sp.batch_size);
+      uint32_t ci = cx.node_count < p.coll_table_len ? cx.node_count : p.coll_table_len - 1;
+      int collisions_left = (int)cx.coll_table[ci];
+      int n_tp = 0;
+      while ((uint32_t)n_tp < bs && collisions_left > 0 && cx.error == 0) {
+        uint32_t budget = min((uint32_t)collisions_left, bs - (uint32_t)n_tp);
+        uint32_t c = pick_nodes<true>(cx, sp, rng, g, turn, budget, n_tp, false, lane);
+        collisions_left -= (int)c;
+        st.coll += c;
+      }
+      if (cx.error) break;
+      __syncwarp();
+      uint32_t evmask = __ballot_sync(FULL, lane < n_tp && cx.tp[lane].kind == 0);
+      uint32_t evmask_hi = n_tp > 32 ? __ballot_sync(FULL, lane + 32 < n_tp && cx.tp[lane + 32].kind == 0) : 0u;
+      const uint32_t n_eval = __popc(evmask) + __popc(evmask_hi);
+      st.n_tp = (uint32_t)n_tp;
+      if (n_eval == 0) {
+        // nothing to evaluate (terminal-only batch): back up at once and keep going
+        for (int e = 0; e < n_tp; ++e) backup_entry(cx, e, 0.0f, 0.0f, nullptr, nullptr, lane);
+        st.term += (uint32_t)n_tp;
+        uint32_t produced = n_tp > 1 ? (uint32_t)n_tp : 1u;
+        st.remaining = st.remaining > produced ? st.remaining - produced : 0u;
+        continue;
+      }
+      uint32_t rb = 0;
+      if (lane == 0) rb = atomicAdd(q.n_rows, n_eval);
+      rb = __shfl_sync(FULL, rb, 0);
+      if (rb + n_eval > q.max_rows) { cx.error = AR_ERR_POOL_OVERFLOW; break; }
+      st.row_base = rb;
+      for (int e = lane; e < n_tp; e += 32) {
+        TpEntry te = cx.tp[e];
+        tp_g[e] = te;
+        if (te.kind == 0) {
+          uint32_t m = e < 32 ? (evmask & ((1u << e) - 1u)) : evmask;
+          uint32_t mh = e < 32 ? 0u : (evmask_hi & ((1u << (e - 32)) - 1u));
+          uint32_t r = rb + __popc(m) + __popc(mh);
+          GPack gp = cx.tp_state[e];
+          EvalRow er;
+          er.cheese = gp.cheese;
+          er.pos = gp.pos;
+          er.score = gp.score;
+          er.game_idx = (uint32_t)st.gi;
+          er.turn = (uint16_t)(turn + te.depth);
+          er.max_turns = (uint16_t)cx.max_turns;
+          er.pad[0] = er.pad[1] = 0;
+          q.rows[r] = er;
+        }
+      }
+      st.phase = PH_WAIT_EVAL;
+      break;
+    }
+  }
+
+  st.g = g_pack(g);
+  st.rng = rng;
+  st.turn = turn;
+  st.epoch = cx.epoch;
+  st.node_count = cx.node_count;
+  st.path_nodes = cx.path_nodes;
+  st.new_nodes = cx.new_nodes;
+  st.error = cx.error;
+  __syncwarp();
+  if (lane == 0) {
+    *sp_g = st;
+    if (st.phase == PH_DONE) {
+      atomicAdd(&p.counters[0], (unsigned long long)cx.path_nodes);
+      atomicAdd(&p.counters[1], (unsigned long long)cx.new_nodes);
+    }
+    if (cx.error) atomicCAS(p.error_flag, 0, (int)cx.error);
+  }
+}
+
 }  // namespace ar
 
 // =========================================================================================
@@ -330,6 +616,13 @@ struct ar_engine {
   EvalRow* d_rows = nullptr;
   float* d_nn_out = nullptr;
   int cap_rows = 0;
+  // NN-mode step state
+  SlotState* d_slots = nullptr;
+  TpEntry* d_tp_store = nullptr;
+  EvalRow* d_queue = nullptr;
+  float* d_queue_out = nullptr;
+  uint32_t* d_n_rows = nullptr;   // [0] queue length, [1] done slots
+  uint64_t nn_steps = 0;
 };
 
 static thread_local std::string g_create_error;
@@ -527,6 +820,7 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
   CKC(cudaHostAlloc(&e->h_progress, sizeof(ar_progress), cudaHostAllocMapped));
   CKC(cudaHostGetDevicePointer(&e->d_progress, e->h_progress, 0));
   CKC(cudaFuncSetAttribute(selfplay_uniform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CKC(cudaFuncSetAttribute(nn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #undef CKC
   *out = e;
   return AR_OK;
@@ -539,6 +833,7 @@ void ar_engine_destroy(ar_engine* e) {
   cudaFree(e->d_games); cudaFree(e->d_seeds); cudaFree(e->d_summaries); cudaFree(e->d_positions);
   cudaFree(e->d_search); cudaFree(e->d_next); cudaFree(e->d_counters); cudaFree(e->d_error);
   cudaFree(e->d_rows); cudaFree(e->d_nn_out);
+  cudaFree(e->d_slots); cudaFree(e->d_tp_store); cudaFree(e->d_queue); cudaFree(e->d_queue_out); cudaFree(e->d_n_rows);
   e->mlp.release();
   if (e->h_progress) cudaFreeHost(e->h_progress);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -595,6 +890,17 @@ static RunParams make_params(ar_engine* e, const ar_search_cfg* cfg) {
   return p;
 }
 
+static ar_status ensure_nn_buffers(ar_engine* e) {
+  if (e->d_slots) return AR_OK;
+  size_t max_rows = (size_t)e->n_slots * e->batch_cap;
+  CK(cudaMalloc(&e->d_slots, (size_t)e->n_slots * sizeof(SlotState)));
+  CK(cudaMalloc(&e->d_tp_store, max_rows * sizeof(TpEntry)));
+  CK(cudaMalloc(&e->d_queue, max_rows * sizeof(EvalRow)));
+  CK(cudaMalloc(&e->d_queue_out, max_rows * 12 * sizeof(float)));
+  CK(cudaMalloc(&e->d_n_rows, 2 * sizeof(uint32_t)));
+  return AR_OK;
+}
+
 static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_progress, float* ms) {
   CK(cudaMemsetAsync(e->d_next, 0, sizeof(unsigned int), e->stream));
   CK(cudaMemsetAsync(e->d_counters, 0, 8 * sizeof(unsigned long long), e->stream));
@@ -605,12 +911,50 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
   int slots = std::min<int>(e->n_slots, std::max(p.n_games, 1));
   p.n_slots = slots;
   int blocks = (slots + 3) / 4;
+  const bool nn = e->arch != AR_ARCH_UNIFORM;
+  if (nn) {
+    ar_status s = ensure_nn_buffers(e);
+    if (s) return s;
+  }
   CK(cudaEventRecord(e->ev0, e->stream));
-  selfplay_uniform_kernel<<<blocks, 128, smem, e->stream>>>(p);
-  CK(cudaGetLastError());
+  if (!nn) {
+    selfplay_uniform_kernel<<<blocks, 128, smem, e->stream>>>(p);
+    CK(cudaGetLastError());
+    e->launches += 1;
+  } else {
+    NnParams q{};
+    q.slots = e->d_slots;
+    q.tp_store = e->d_tp_store;
+    q.rows = e->d_queue;
+    q.n_rows = e->d_n_rows;
+    q.nn_out = e->d_queue_out;
+    q.done_slots = e->d_n_rows + 1;
+    q.max_rows = (uint32_t)((size_t)slots * e->batch_cap);
+    CK(cudaMemsetAsync(e->d_n_rows, 0, 2 * sizeof(uint32_t), e->stream));
+    nn_init_slots_kernel<<<(slots + 127) / 128, 128, 0, e->stream>>>(e->d_slots, slots);
+    CK(cudaGetLastError());
+    e->launches += 1;
+    const int check_every = 32;
+    for (;;) {
+      for (int it = 0; it < check_every; ++it) {
+        CK(cudaMemsetAsync(e->d_n_rows, 0, sizeof(uint32_t), e->stream));
+        nn_step_kernel<<<blocks, 128, smem, e->stream>>>(p, q);
+        CK(cudaGetLastError());
+        CK(e->mlp.forward(e->d_queue, e->d_n_rows, (int)q.max_rows, p.games, e->d_queue_out, e->d_error, e->stream));
+        e->launches += 2;
+        e->nn_steps += 1;
+      }
+      uint32_t h[2] = {0, 0};
+      int herr = 0;
+      CK(cudaMemcpyAsync(h, e->d_n_rows, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaMemcpyAsync(&herr, e->d_error, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+      CK(cudaStreamSynchronize(e->stream));
+      if (user_progress) memcpy((void*)user_progress, (const void*)e->h_progress, sizeof(ar_progress));
+      if (herr != 0 || (int)h[1] >= slots) break;
+    }
+  }
   CK(cudaEventRecord(e->ev1, e->stream));
-  e->launches += 1;
-  if (user_progress) {
+  if (user_progress && !nn) {
     while (cudaEventQuery(e->ev1) == cudaErrorNotReady) {
       memcpy((void*)user_progress, (const void*)e->h_progress, sizeof(ar_progress));
       std::this_thread::sleep_for(std::chrono::milliseconds(2));
@@ -623,7 +967,8 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
   CK(cudaMemcpy(&herr, e->d_error, sizeof(int), cudaMemcpyDeviceToHost));
   if (herr != 0) {
     e->err = "device reported status " + std::to_string(herr) +
-             (herr == AR_ERR_POOL_OVERFLOW ? " (node pool / depth stack exhausted: raise pool_nodes or max_turns)" : "");
+             (herr == AR_ERR_POOL_OVERFLOW ? " (node pool / depth stack / eval queue exhausted: raise pool_nodes or max_turns)"
+              : herr == AR_ERR_NONFINITE ? " (the evaluator produced a non-finite value)" : "");
     return (ar_status)herr;
   }
   return AR_OK;
@@ -640,6 +985,12 @@ ar_status ar_search_batch(ar_engine* e, const ar_game_pod* games, int32_t n, con
   if (n == 0) return AR_OK;
   if (!seeds || !out) { e->err = "seeds/out is NULL"; return AR_ERR_INVALID_ARG; }
   if ((uint64_t)cfg->simulations + 2 > e->pool_nodes) { e->err = "simulations exceed pool_nodes"; return AR_ERR_POOL_OVERFLOW; }
+  if (e->arch != AR_ARCH_UNIFORM)
+    for (int i = 0; i < n; ++i)
+      if (games[i].width != e->nn_width || games[i].height != e->nn_height) {
+        e->err = "game board size does not match the loaded evaluator";
+        return AR_ERR_INVALID_ARG;
+      }
   s = ensure_coll_table(e, *cfg);
   if (s) return s;
   if (n > e->cap_games) {
@@ -705,8 +1056,15 @@ static ar_status run_resident(ar_engine* e, const ar_search_cfg* cfg, ar_progres
   if (s) return s;
   s = ensure_coll_table(e, *cfg);
   if (s) return s;
+  if (e->arch != AR_ARCH_UNIFORM)
+    for (const ar_game_pod& g : e->h_games)
+      if (g.width != e->nn_width || g.height != e->nn_height) {
+        e->err = "game board size does not match the loaded evaluator";
+        return AR_ERR_INVALID_ARG;
+      }
   int n = e->n_resident;
   float ms = 0;
+  e->launches = 0;
   RunParams p = make_params(e, cfg);
   if (n > 0) {
     p.games = e->d_games; p.seeds = e->d_seeds; p.n_games = n;
@@ -723,7 +1081,7 @@ static ar_status run_resident(ar_engine* e, const ar_search_cfg* cfg, ar_progres
     stats->device_ms = ms;
     stats->path_nodes = c[0];
     stats->new_nodes = c[1];
-    stats->kernel_launches = n > 0 ? 1 : 0;
+    stats->kernel_launches = e->launches;
 #ifdef AR_PHASE_TIMING
     fprintf(stderr, "[phase cycles] gather=%llu backup=%llu advance=%llu total=%llu\n", c[2], c[3], c[4], c[5]);
 #endif

@@ -1,0 +1,116 @@
+"""NN-guided search and self-play on the GPU against the oracle.
+
+Two gates:
+  1. tree logic: the oracle is driven by the GPU evaluator itself (predict_fn-style callback that
+     calls `ar_nn_forward`), so both sides see identical priors and values and every output must
+     match bit-for-bit — populate_node reduction order, backup chain order, VL bookkeeping, the
+     cross-game evaluation queue and tree reuse included.
+  2. end-to-end numerics: the oracle is driven by the fp32 restatement of the reference model
+     (validated against the real reference in tests/test_oracle_golden.py).  Visit tables are no
+     longer identical; the stated tolerance is on the median / 90th percentile of L1(policy) and
+     of |value| error / max(1, |v|) over 64 positions (see the constants below).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from alpharat_b200 import _native as N
+from alpharat_b200.engine import Engine, search_cfg
+from alpharat_b200.games import make_games, pods_array
+from conftest import EVAL_CB, oracle_search, oracle_selfplay
+from nn_ref import make_mlp_state_dict, mlp_forward, random_positions
+from test_gpu_parity_uniform import assert_result_equal, compare_selfplay
+
+pytestmark = pytest.mark.gpu
+
+# Stated tolerances of the end-to-end gate (bf16 evaluator vs fp32 reference, 400-sim searches).
+# A search is a discontinuous function of its priors: at near-ties between two moves a 1e-3
+# change of a prior can flip the visit-proportional policy (L1 up to 2), so the gate is on the
+# median and the 90th percentile over 64 positions; the maximum is reported, not bounded.
+L1_MEDIAN_TOL, L1_P90_TOL = 0.02, 0.15
+V_MEDIAN_TOL, V_P90_TOL = 0.01, 0.06
+
+
+def gpu_eval_callback(eng):
+    def cb(user, states, n, p1, p2, v1, v2):
+        pods = (N.GamePod * n).from_address(C.addressof(states.contents))
+        a, b, c, d = eng.nn_forward(pods)
+        C.memmove(p1, a.ctypes.data, n * 20)
+        C.memmove(p2, b.ctypes.data, n * 20)
+        C.memmove(v1, c.ctypes.data, n * 4)
+        C.memmove(v2, d.ctypes.data, n * 4)
+        return 0
+
+    return EVAL_CB(cb)
+
+
+def test_nn_search_bit_exact_with_shared_evaluator(oracle):
+    specs = make_games(12, width=7, height=7, cheese_count=10, max_turns=50) + random_positions(12, 7, 7, seed=5)
+    pods = pods_array(specs)
+    sd = make_mlp_state_dict(0, 349)
+    for sims, bs in ((64, 8), (400, 16)):
+        cfg = search_cfg(simulations=sims, batch_size=bs, c_puct=0.512, fpu_reduction=0.459, force_k=0.103)
+        seeds = [11 * i + sims for i in range(len(specs))]
+        with Engine(concurrent_games=16, max_turns=100, max_batch_size=16, max_simulations=sims, pool_nodes=4096) as eng:
+            eng.load_weights(N.AR_ARCH_MLP, 7, 7, sd)
+            out = eng.search_batch(pods, cfg, seeds)
+            cb = gpu_eval_callback(eng)
+            for i in range(len(specs)):
+                rc, ref, clean = oracle_search(oracle, pods[i], cfg, seeds[i], eval_cb=cb)
+                assert rc == 0 and clean
+                assert_result_equal(out[i], ref, f"sims={sims} pos {i}")
+
+
+def test_nn_selfplay_bit_exact_with_shared_evaluator(oracle):
+    n = 6
+    specs = make_games(n, width=7, height=7, cheese_count=10, max_turns=30, first_index=500)
+    pods = pods_array(specs)
+    sd = make_mlp_state_dict(1, 349)
+    cfg = search_cfg(simulations=200, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103)
+    seeds = [900 + i for i in range(n)]
+    with Engine(concurrent_games=4, max_turns=30, max_batch_size=16, max_simulations=200, pool_nodes=8192) as eng:
+        eng.load_weights(N.AR_ARCH_MLP, 7, 7, sd)
+        gpu = eng.selfplay(pods, cfg, seeds)
+        cpu = oracle_selfplay(oracle, pods, cfg, seeds, n_threads=1, eval_cb=gpu_eval_callback(eng))
+    compare_selfplay(gpu, cpu, n)
+    assert gpu[3].total_nn_evals > 0 and gpu[3].kernel_launches > 2
+
+
+def test_nn_search_within_tolerance_of_fp32_reference(oracle):
+    specs = make_games(64, width=7, height=7, cheese_count=10, max_turns=50, first_index=77)
+    pods = pods_array(specs)
+    sd = make_mlp_state_dict(0, 349)
+    cfg = search_cfg(simulations=400, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103)
+    seeds = list(range(64))
+
+    def cb(user, states, n, p1, p2, v1, v2):
+        sub = (N.GamePod * n).from_address(C.addressof(states.contents))
+        obs = np.zeros((n, 349), np.float32)
+        oracle.orc_encode(sub, n, obs.ctypes.data_as(C.POINTER(C.c_float)))
+        a, b, c, d = mlp_forward(sd, obs)
+        for dst, src in ((p1, a), (p2, b), (v1, c), (v2, d)):
+            src = np.ascontiguousarray(src, np.float32)
+            C.memmove(dst, src.ctypes.data, src.nbytes)
+        return 0
+
+    cbp = EVAL_CB(cb)
+    with Engine(concurrent_games=16, max_turns=50, max_batch_size=16, max_simulations=400, pool_nodes=4096) as eng:
+        eng.load_weights(N.AR_ARCH_MLP, 7, 7, sd)
+        out = eng.search_batch(pods, cfg, seeds)
+    l1, verr = [], []
+    for i in range(64):
+        rc, ref, _ = oracle_search(oracle, pods[i], cfg, seeds[i], eval_cb=cbp)
+        assert rc == 0
+        for a, b in ((out[i].policy_p1, ref.policy_p1), (out[i].policy_p2, ref.policy_p2)):
+            l1.append(float(np.abs(np.asarray(a[:]) - np.asarray(b[:])).sum()))
+        for a, b in ((out[i].value_p1, ref.value_p1), (out[i].value_p2, ref.value_p2)):
+            verr.append(abs(a - b) / max(1.0, abs(b)))
+        assert out[i].total_visits == ref.total_visits == 400
+    print(f"policy L1: median {np.median(l1):.4f} p90 {np.percentile(l1, 90):.4f} max {np.max(l1):.4f}; "
+          f"value rel err: median {np.median(verr):.4f} p90 {np.percentile(verr, 90):.4f} max {np.max(verr):.4f}")
+    assert np.median(l1) <= L1_MEDIAN_TOL and np.percentile(l1, 90) <= L1_P90_TOL, l1
+    assert np.median(verr) <= V_MEDIAN_TOL and np.percentile(verr, 90) <= V_P90_TOL, verr
