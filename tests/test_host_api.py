@@ -1,0 +1,146 @@
+"""Host-side mirror of the reference interface: config, C-ABI surface, game generator, bundles."""
+
+from __future__ import annotations
+
+import ctypes as C
+import inspect
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+from pydantic import TypeAdapter, ValidationError
+
+import alpharat_b200 as ab
+from alpharat_b200 import _native as N
+from alpharat_b200.bundle import BUNDLE_KEYS, write_bundles
+from alpharat_b200.engine import search_cfg
+from alpharat_b200.games import GameSpec, make_games, maze_array, pods_array
+from conftest import oracle_selfplay
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_config_is_a_discriminated_union_and_round_trips():
+    ta = TypeAdapter(ab.MCTSConfig)
+    cuda = ta.validate_python({"backend": "cuda", "simulations": 1897, "c_puct": 0.512, "batch_size": 16})
+    assert isinstance(cuda, ab.CudaMCTSConfig) and cuda.simulations == 1897
+    rust = ta.validate_python({"backend": "rust", "simulations": 554})
+    assert isinstance(rust, ab.RustMCTSConfig)
+    assert ta.validate_python(cuda.model_dump()) == cuda  # batch metadata / manifest round trip
+    with pytest.raises(ValidationError):
+        ta.validate_python({"backend": "cuda", "not_a_field": 1})  # extra='forbid' like the reference
+    assert set(ab.RustMCTSConfig.model_fields) - {"backend"} <= set(ab.CudaMCTSConfig.model_fields)
+    noisy = ab.CudaMCTSConfig(noise_epsilon=0.25)
+    assert noisy.for_evaluation().noise_epsilon == 0.0 and ab.CudaMCTSConfig().for_evaluation().noise_epsilon == 0.0
+
+
+def test_self_play_signature_covers_rust_self_play():
+    """Every keyword of rust_self_play (crates/alpharat-sampling/src/bindings.rs:268-304) is accepted."""
+    ref = ("width height cheese_count max_turns num_games cheese_symmetric maze_type positions wall_density "
+           "mud_density maze_symmetric simulations batch_size c_puct fpu_reduction force_k noise_epsilon "
+           "noise_concentration collision_limit_min collision_limit_max collision_scaling_start "
+           "collision_scaling_end collision_scaling_power num_threads output_dir max_games_per_bundle "
+           "onnx_model_path device mux_max_batch_size cache_size progress").split()
+    params = inspect.signature(ab.cuda_self_play).parameters
+    assert [p for p in ref if p not in params] == []
+    assert all(p.kind is inspect.Parameter.KEYWORD_ONLY for p in params.values())
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    so = N.library_path()
+    if not so.exists():
+        subprocess.run(["python", "-m", "alpharat_b200.build"], check=True, cwd=ROOT)
+    lib = N.load_library()
+    header = (ROOT / "include" / "alpharat_cuda.h").read_text()
+    for sym in N.EXPORTED_SYMBOLS:
+        assert sym + "(" in header.replace(" (", "("), f"{sym} not declared in the header"
+        assert getattr(lib, sym) is not None
+    assert lib.ar_abi_version() == N.AR_ABI_VERSION
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setenv("ALPHARAT_CUDA_LIB", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(N, "_LIB", None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        N.load_library()
+
+
+def test_pod_layout_matches_the_c_header(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu %%zu", '
+                   "sizeof(ar_game_pod),sizeof(ar_search_cfg),sizeof(ar_search_result),sizeof(ar_position_record),"
+                   "sizeof(ar_game_summary),sizeof(ar_stats),sizeof(ar_progress),sizeof(ar_engine_cfg),sizeof(ar_tensor_desc));}"
+                   % (ROOT / "include" / "alpharat_cuda.h"))
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", str(src), "-o", str(exe)], check=True)
+    sizes = list(map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()))
+    py = [C.sizeof(t) for t in (N.GamePod, N.SearchCfg, N.SearchResultPod, N.PositionRecord, N.GameSummary,
+                                N.Stats, N.Progress, N.EngineCfg, N.TensorDesc)]
+    assert sizes == py
+
+
+def test_game_generator_properties():
+    specs = make_games(200, width=7, height=7, cheese_count=10, max_turns=50)
+    again = make_games(200, width=7, height=7, cheese_count=10, max_turns=50)
+    for a, b in zip(specs, again):
+        assert a.cheese == b.cheese  # SplitMix64(game_index): reproducible
+    for s in specs:
+        cells = set(s.cheese)
+        assert len(cells) == 10 and (0, 0) not in cells and (6, 6) not in cells
+        assert all((6 - x, 6 - y) in cells for x, y in cells)  # 180-degree symmetry
+    odd = make_games(20, width=5, height=5, cheese_count=5, max_turns=30)
+    assert all((2, 2) in s.cheese for s in odd)  # odd symmetric count uses the centre
+    assert len({tuple(sorted(s.cheese)) for s in specs}) > 150
+    shifted = make_games(3, width=7, height=7, cheese_count=10, max_turns=50, first_index=5)
+    assert shifted[0].cheese == specs[5].cheese
+    with pytest.raises(ValueError):
+        make_games(1, width=5, height=5, cheese_count=5, max_turns=30, maze_type="random")
+
+
+def test_maze_array_and_pod_packing():
+    spec = GameSpec(5, 5, 100, (1, 0), (4, 4), [(4, 0)], walls=[((2, 2), (2, 3))], mud=[((1, 0), (2, 0), 3)])
+    m = maze_array(spec)
+    assert m.shape == (5, 5, 4) and m.dtype == np.int8
+    assert m[0, 0, 2] == -1 and m[0, 0, 3] == -1 and m[4, 4, 0] == -1 and m[4, 4, 1] == -1
+    assert m[2, 2, 0] == -1 and m[3, 2, 2] == -1  # wall both ways
+    assert m[0, 1, 1] == 3 and m[0, 2, 3] == 3  # mud both ways
+    assert m[1, 1, 0] == 1
+    pod = pods_array([spec])[0]
+    assert (pod.width, pod.height, pod.p1_x, pod.p2_y, pod.max_turns) == (5, 5, 1, 4, 100)
+    assert pod.cheese[0] == 1 << 4 and sum(pod.cheese) == 16
+    assert pod.move_cost[(0 * 5 + 1) * 4 + 1] == 3 and pod.move_cost[(2 * 5 + 2) * 4 + 0] == 0
+
+
+def test_bundle_format(oracle, tmp_path):
+    """The 26 keys, dtypes and shapes of write_bundle (recording.rs:139-166; test_rust_sampling.py:115-213)."""
+    n = 7
+    specs = make_games(n, width=5, height=5, cheese_count=5, max_turns=30)
+    pods = pods_array(specs)
+    summ, pos, stride, st = oracle_selfplay(oracle, pods, search_cfg(simulations=50), list(range(n)), n_threads=2)
+    paths = write_bundles(tmp_path / "games", specs, summ, pos, stride, max_games_per_bundle=3)
+    assert len(paths) == 3 and all(p.name.startswith("bundle_") and p.suffix == ".npz" for p in paths)
+    assert not list((tmp_path / "games").glob("*.tmp"))
+    total_games = total_pos = 0
+    for p in paths:
+        z = np.load(p)
+        assert set(z.files) == set(BUNDLE_KEYS) and len(BUNDLE_KEYS) == 26
+        k, npos = len(z["game_lengths"]), int(z["game_lengths"].sum())
+        total_games += k
+        total_pos += npos
+        assert z["game_lengths"].dtype == np.int32 and z["maze"].dtype == np.int8 and z["maze"].shape == (k, 5, 5, 4)
+        assert z["initial_cheese"].dtype == np.bool_ and z["initial_cheese"].shape == (k, 5, 5)
+        assert z["cheese_outcomes"].dtype == np.int8 and z["max_turns"].dtype == np.int16 and z["result"].dtype == np.int8
+        assert z["final_p1_score"].dtype == np.float32
+        assert z["p1_pos"].shape == (npos, 2) and z["p1_pos"].dtype == np.int8
+        assert z["cheese_mask"].shape == (npos, 5, 5) and z["cheese_mask"].dtype == np.bool_
+        assert z["turn"].dtype == np.int16 and z["action_p1"].dtype == np.int8
+        for key in ("visit_counts_p1", "prior_p2", "policy_p1"):
+            assert z[key].shape == (npos, 5) and z[key].dtype == np.float32
+        assert z["value_p1"].shape == (npos,)
+        assert np.allclose(z["policy_p1"].sum(1), 1, atol=1e-5)
+        assert (z["initial_cheese"].sum((1, 2)) == 5).all()
+        first = np.cumsum(np.concatenate([[0], z["game_lengths"][:-1]]))
+        assert (z["cheese_mask"][first] == z["initial_cheese"]).all() and (z["turn"][first] == 0).all()
+        assert set(np.unique(z["cheese_outcomes"])) <= {0, 1, 2, 3}
+    assert total_games == n and total_pos == st.total_positions
