@@ -375,7 +375,8 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
   }
   TpEntry* tp_g = q.tp_store + (size_t)slot * p.batch_cap;
 
-  for (int iter = 0; iter < 6 && cx.error == 0; ++iter) {
+  bool moved = false;
+  for (int iter = 0; iter < 3 && cx.error == 0; ++iter) {
     if (st.phase == PH_IDLE) {
       unsigned int gi = 0;
       if (lane == 0) gi = atomicAdd(p.next_game, 1u);
@@ -468,6 +469,7 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
             cx.epoch += 1;
             init_root(cx, g, lane);
           }
+          moved = true;
         }
         if (game_over(g, turn, cx.max_turns)) {
           if (lane == 0) {
@@ -496,6 +498,9 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
         }
         st.remaining = sp.n_sims;
         st.nn = st.term = st.coll = 0;
+        // the step is bulk-synchronous: a slot that just compacted its tree gathers next step,
+        // so the step's critical path is max(backup + advance, backup + gather), not their sum
+        if (moved) break;
       }
       // ---- gather one batch (simulate_batch up to the evaluator, search.rs:961-1023)
       cx.epoch += 1;
