@@ -95,6 +95,7 @@ __device__ __forceinline__ void simulate_batch_uniform(WarpCtx& cx, const Search
   for (int e = 0; e < n_tp; ++e) {
     uint8_t kind = cx.tp[e].kind;
     if (kind == 1) term += 1; else nn += 1;
+    if (kind == 0 && cx.tp[e].node == 0 && sp.noise_epsilon > 0.0f) apply_root_noise(cx, sp, rng, lane);
     backup_entry(cx, e, 0.0f, 0.0f, nullptr, nullptr, lane);
   }
   AR_T1(1);
@@ -411,7 +412,14 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
           const float* o = q.nn_out + (size_t)row * 12;
           row += 1;
           nn_b += 1;
-          backup_entry(cx, e, o[10], o[11], o, o + 5, lane);
+          if (cx.tp[e].node == 0 && sp.noise_epsilon > 0.0f) {
+            // populate first, then noise, then backup (search.rs:1034-1052)
+            backup_entry(cx, e, o[10], o[11], o, o + 5, lane, /*populate_only=*/true);
+            apply_root_noise(cx, sp, rng, lane);
+            backup_entry(cx, e, o[10], o[11], nullptr, nullptr, lane);
+          } else {
+            backup_entry(cx, e, o[10], o[11], o, o + 5, lane);
+          }
         } else {
           term_b += 1;
           backup_entry(cx, e, 0.0f, 0.0f, nullptr, nullptr, lane);
@@ -683,10 +691,6 @@ static ar_status validate_cfg(ar_engine* e, const ar_search_cfg* c) {
     e->err = "batch_size " + std::to_string(c->batch_size) + " outside [1, engine max_batch_size=" +
              std::to_string(e->batch_cap) + "]";
     return AR_ERR_INVALID_ARG;
-  }
-  if (c->noise_epsilon > 0.0f) {
-    e->err = "noise_epsilon > 0 (Dirichlet root noise) is not implemented in this build";
-    return AR_ERR_UNSUPPORTED;
   }
   if (c->collision_limit_max + 2 * c->batch_size > 1023u) {
     e->err = "collision_limit_max + 2 * batch_size must be <= 1023 (10-bit in-flight counters)";

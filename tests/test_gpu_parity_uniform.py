@@ -126,3 +126,28 @@ def test_large_scale_properties():
         collected = sum(1 for c in bytes(s.cheese_outcomes)[:49] if c != 2)
         assert collected == s.final_p1_score + s.final_p2_score
     assert st.total_games == n
+
+
+def test_selfplay_with_dirichlet_noise(oracle):
+    """Production sampling config (`7x7_rust_tuned.yaml`: noise_epsilon 0.25, concentration 10.83).
+
+    The Gamma sampler is the oracle's restatement (Marsaglia-Tsang over a polar normal), drawn
+    from the same per-game stream, so GPU and oracle agree draw for draw; against the real
+    reference (rand_distr's ziggurat) the noise agrees in distribution only.
+    """
+    n = 24
+    specs = make_games(n, width=7, height=7, cheese_count=10, max_turns=50, first_index=300)
+    pods = pods_array(specs)
+    cfg = search_cfg(simulations=600, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103,
+                     noise_epsilon=0.25, noise_concentration=10.83)
+    seeds = [5000 + i for i in range(n)]
+    with Engine(concurrent_games=n, max_turns=50, max_batch_size=16, max_simulations=600) as eng:
+        gpu = eng.selfplay(pods, cfg, seeds)
+        quiet = eng.selfplay(pods, search_cfg(simulations=600, batch_size=16, c_puct=0.512,
+                                              fpu_reduction=0.459, force_k=0.103), seeds)
+    cpu = oracle_selfplay(oracle, pods, cfg, seeds)
+    compare_selfplay(gpu, cpu, n)
+    # the noise is really applied: root priors of the first move are no longer uniform
+    pri = np.array(gpu[1][0].search.prior_p1[:])
+    assert abs(pri.sum() - 1.0) < 1e-5 and pri.std() > 1e-3
+    assert list(quiet[1][0].search.prior_p1[:]) != list(gpu[1][0].search.prior_p1[:])
