@@ -23,6 +23,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-
 UNITS = [
     ("engine.cu", ["-fmad=false"]),
     ("nn_kernels.cu", []),
+    ("nn_symmetric.cu", []),
+    ("nn_cnn.cu", []),
 ]
 
 

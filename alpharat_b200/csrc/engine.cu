@@ -625,7 +625,7 @@ struct ar_engine {
   // leaf evaluator
   int arch = AR_ARCH_UNIFORM;
   int nn_width = 0, nn_height = 0;
-  MlpModel mlp;
+  LeafEvaluator* eval = nullptr;
   EvalRow* d_rows = nullptr;
   float* d_nn_out = nullptr;
   int cap_rows = 0;
@@ -843,7 +843,7 @@ void ar_engine_destroy(ar_engine* e) {
   cudaFree(e->d_search); cudaFree(e->d_next); cudaFree(e->d_counters); cudaFree(e->d_error);
   cudaFree(e->d_rows); cudaFree(e->d_nn_out);
   cudaFree(e->d_slots); cudaFree(e->d_tp_store); cudaFree(e->d_queue); cudaFree(e->d_queue_out); cudaFree(e->d_n_rows);
-  e->mlp.release();
+  delete e->eval;
   if (e->h_progress) cudaFreeHost(e->h_progress);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
@@ -855,19 +855,21 @@ ar_status ar_engine_load_weights(ar_engine* e, int32_t arch, int32_t width, int3
                                  const ar_tensor_desc* tensors, int32_t n_tensors) {
   if (!e) return AR_ERR_INVALID_ARG;
   CK(cudaSetDevice(e->device));
-  if (arch == AR_ARCH_UNIFORM) {
-    e->mlp.release();
-    e->arch = AR_ARCH_UNIFORM;
-    return AR_OK;
-  }
-  if (arch != AR_ARCH_MLP) {
-    e->err = "architecture " + std::to_string(arch) + " has no CUDA evaluator in this build (MLP only)";
+  delete e->eval;
+  e->eval = nullptr;
+  e->arch = AR_ARCH_UNIFORM;
+  if (arch == AR_ARCH_UNIFORM) return AR_OK;
+  if (arch != AR_ARCH_MLP && arch != AR_ARCH_SYMMETRIC && arch != AR_ARCH_CNN) {
+    e->err = "unknown architecture " + std::to_string(arch);
     return AR_ERR_UNSUPPORTED;
   }
   if (width <= 0 || height <= 0 || width * height > 64) { e->err = "bad board size"; return AR_ERR_INVALID_ARG; }
   if (!tensors || n_tensors <= 0) { e->err = "no tensors"; return AR_ERR_INVALID_ARG; }
-  int rc = e->mlp.load(tensors, n_tensors, width, height, e->err);
-  if (rc != AR_OK) return (ar_status)rc;
+  LeafEvaluator* ev = arch == AR_ARCH_MLP ? static_cast<LeafEvaluator*>(new MlpModel())
+                      : arch == AR_ARCH_SYMMETRIC ? make_symmetric_evaluator() : make_cnn_evaluator();
+  int rc = ev->load(tensors, n_tensors, width, height, e->err);
+  if (rc != AR_OK) { delete ev; return (ar_status)rc; }
+  e->eval = ev;
   e->arch = arch;
   e->nn_width = width;
   e->nn_height = height;
@@ -949,7 +951,7 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
         CK(cudaMemsetAsync(e->d_n_rows, 0, sizeof(uint32_t), e->stream));
         nn_step_kernel<<<blocks, 128, smem, e->stream>>>(p, q);
         CK(cudaGetLastError());
-        CK(e->mlp.forward(e->d_queue, e->d_n_rows, (int)q.max_rows, p.games, e->d_queue_out, e->d_error, e->stream));
+        CK(e->eval->forward(e->d_queue, e->d_n_rows, (int)q.max_rows, p.games, e->d_queue_out, e->d_error, e->stream));
         e->launches += 2;
         e->nn_steps += 1;
       }
@@ -1226,7 +1228,7 @@ ar_status ar_nn_forward(ar_engine* e, const ar_game_pod* games, int32_t n, float
                         float* value_p1, float* value_p2) {
   if (!e) return AR_ERR_INVALID_ARG;
   CK(cudaSetDevice(e->device));
-  if (e->arch == AR_ARCH_UNIFORM || !e->mlp.loaded) { e->err = "no evaluator loaded (ar_engine_load_weights)"; return AR_ERR_NO_WEIGHTS; }
+  if (e->arch == AR_ARCH_UNIFORM || !e->eval) { e->err = "no evaluator loaded (ar_engine_load_weights)"; return AR_ERR_NO_WEIGHTS; }
   if (n == 0) return AR_OK;
   if (!policy_p1 || !policy_p2 || !value_p1 || !value_p2) { e->err = "output is NULL"; return AR_ERR_INVALID_ARG; }
   ar_status s = stage_rows(e, games, n);
@@ -1237,7 +1239,7 @@ ar_status ar_nn_forward(ar_engine* e, const ar_game_pod* games, int32_t n, float
       return AR_ERR_INVALID_ARG;
     }
   CK(cudaMemsetAsync(e->d_error, 0, sizeof(int), e->stream));
-  CK(e->mlp.forward(e->d_rows, nullptr, n, e->d_games, e->d_nn_out, e->d_error, e->stream));
+  CK(e->eval->forward(e->d_rows, nullptr, n, e->d_games, e->d_nn_out, e->d_error, e->stream));
   std::vector<float> out((size_t)n * 12);
   CK(cudaMemcpyAsync(out.data(), e->d_nn_out, out.size() * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   int herr = 0;

@@ -31,17 +31,32 @@ struct MlpWeights {
   int k1_blocks;
 };
 
-struct MlpModel {
+// A loaded leaf evaluator (replaces `dyn Backend`, crates/alpharat-mcts/src/backend.rs:75-82, for the
+// NN-guided mode).  forward() scores `rows` into out[row][12] = policy_p1[5], policy_p2[5], v1, v2.
+// n_rows_dev != nullptr: the row count is read on device (the self-play loop never syncs).
+struct LeafEvaluator {
+  virtual ~LeafEvaluator() {}
+  virtual int load(const ar_tensor_desc* tensors, int n, int width, int height, std::string& err) = 0;
+  virtual cudaError_t forward(const EvalRow* rows, const uint32_t* n_rows_dev, int n_rows_max,
+                              const ar_game_pod* games, float* out, int* error_flag,
+                              cudaStream_t stream) const = 0;
+};
+
+struct MlpModel : LeafEvaluator {
   uint8_t *d_w1 = nullptr, *d_w2 = nullptr, *d_w3 = nullptr;
   float* d_b = nullptr;
   int k1_blocks = 0, obs_dim = 0, n_sms = 148;
   size_t smem_bytes = 0;
   bool loaded = false;
-  int load(const ar_tensor_desc* tensors, int n, int width, int height, std::string& err);
+  ~MlpModel() override { release(); }
+  int load(const ar_tensor_desc* tensors, int n, int width, int height, std::string& err) override;
   cudaError_t forward(const EvalRow* rows, const uint32_t* n_rows_dev, int n_rows_max,
-                      const ar_game_pod* games, float* out, int* error_flag, cudaStream_t stream) const;
+                      const ar_game_pod* games, float* out, int* error_flag, cudaStream_t stream) const override;
   void release();
 };
+
+LeafEvaluator* make_symmetric_evaluator();  // nn_symmetric.cu
+LeafEvaluator* make_cnn_evaluator();        // nn_cnn.cu
 
 cudaError_t encode_f32(const EvalRow* rows, int n, const ar_game_pod* games, int obs_dim, float* out,
                        cudaStream_t stream);

@@ -12,4 +12,4 @@ eng.selfplay_upload(pods, list(range(n)))
 st = eng.selfplay_run_resident(cfg)
 summ, pos = eng.selfplay_download(n, mt)
 npos = sum(summ[i].n_positions for i in range(n))
-print(f"n={n} conc={conc} mt={mt} device_ms={st.device_ms:.1f} positions={npos} S_new/s={npos*1897/st.device_ms*1e3:.3e}")
+print(f"n={n} conc={conc} mt={mt} device_ms={st.device_ms:.1f} positions={npos} S_new/s={npos*1897/st.device_ms*1e3:.3e} path_nodes={st.path_nodes} new_nodes={st.new_nodes} algo_bytes={288*st.path_nodes+240*st.new_nodes}")

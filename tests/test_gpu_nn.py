@@ -17,7 +17,8 @@ import pytest
 from alpharat_b200 import _native as N
 from alpharat_b200.engine import Engine
 from alpharat_b200.games import GameSpec, pods_array
-from nn_ref import make_mlp_state_dict, mlp_forward, random_positions
+from nn_ref import (cnn_forward, make_cnn_state_dict, make_mlp_state_dict, make_symmetric_state_dict, mlp_forward,
+                    random_positions, symmetric_forward)
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).resolve().parent / "golden"
@@ -74,6 +75,76 @@ def test_mlp_forward_matches_reference(n):
         assert (np.abs(v - g) <= 4e-3 * np.maximum(1.0, np.abs(g))).all()
     assert np.allclose(p1.sum(1), 1, atol=1e-5) and np.allclose(p2.sum(1), 1, atol=1e-5)
     assert (v1 >= 0).all() and (v2 >= 0).all()
+
+
+def _check_vs_fp32(out, ref, tol_p, tol_v, tag):
+    p1, p2, v1, v2 = out
+    assert np.abs(p1 - ref[0]).max() <= tol_p, (tag, float(np.abs(p1 - ref[0]).max()))
+    assert np.abs(p2 - ref[1]).max() <= tol_p, (tag, float(np.abs(p2 - ref[1]).max()))
+    for v, g in ((v1, ref[2]), (v2, ref[3])):
+        err = np.abs(v - g) / np.maximum(1.0, np.abs(g))
+        assert err.max() <= tol_v, (tag, float(err.max()))
+    assert np.allclose(p1.sum(1), 1, atol=1e-5) and np.allclose(p2.sum(1), 1, atol=1e-5)
+    assert (v1 >= 0).all() and (v2 >= 0).all()
+
+
+def _positions(w, h, n):
+    base = random_positions(96, 7, 7, seed=123) if (w, h) == (7, 7) else random_positions(40, w, h, seed=321)
+    return [base[i % len(base)] for i in range(n)], len(base)
+
+
+@pytest.mark.parametrize("w,h,n", [(7, 7, 1), (7, 7, 96), (7, 7, 64), (7, 7, 65), (7, 7, 1000), (5, 5, 40), (5, 5, 333)])
+def test_symmetric_forward_matches_reference(w, h, n):
+    """SymmetricMLP on tcgen05 vs the real reference's fp32 outputs (goldens) — stated tolerance for bf16
+    operands: |d policy| <= 2.5e-2, |d value| <= 4e-2 * max(1, |v|)."""
+    specs, nb = _positions(w, h, n)
+    sd = make_symmetric_state_dict(2, w, h)
+    g = np.load(GOLD / f"symmetric_{w}x{h}.npz")
+    idx = np.arange(n) % nb
+    with Engine(concurrent_games=4, max_turns=120) as eng:
+        eng.load_weights(N.AR_ARCH_SYMMETRIC, w, h, sd)
+        out = eng.nn_forward(pods_array(specs))
+    _check_vs_fp32(out, [g[k][idx] for k in ("policy_p1", "policy_p2", "value_p1", "value_p2")], 2.5e-2, 4e-2,
+                   f"symmetric {w}x{h} n={n}")
+
+
+def test_symmetric_swaps_outputs_when_players_swap():
+    """Structural P1/P2 symmetry (symmetric.py:20-24): the two-rows-per-position mapping must keep it exactly."""
+    specs, _ = _positions(7, 7, 96)
+    swapped = [GameSpec(s.width, s.height, s.max_turns, s.p2, s.p1, s.cheese, walls=s.walls, mud=s.mud, turn=s.turn,
+                        p1_score=s.p2_score, p2_score=s.p1_score, p1_mud=s.p2_mud, p2_mud=s.p1_mud) for s in specs]
+    with Engine(concurrent_games=4, max_turns=120) as eng:
+        eng.load_weights(N.AR_ARCH_SYMMETRIC, 7, 7, make_symmetric_state_dict(2, 7, 7))
+        a = eng.nn_forward(pods_array(specs))
+        b = eng.nn_forward(pods_array(swapped))
+    assert np.array_equal(a[0], b[1]) and np.array_equal(a[1], b[0])
+    assert np.array_equal(a[2], b[3]) and np.array_equal(a[3], b[2])
+
+
+@pytest.mark.parametrize("tag,blocks", [("gpool", ("res", "res", "gpool")), ("res", ("res",))])
+@pytest.mark.parametrize("w,h,n", [(7, 7, 1), (7, 7, 96), (7, 7, 3), (7, 7, 601), (5, 5, 40), (5, 5, 333)])
+def test_cnn_forward_matches_reference(tag, blocks, w, h, n):
+    """PyRatCNN (configs/model/cnn_gpool.yaml and cnn.yaml trunks) as an implicit GEMM on tcgen05 vs the real
+    reference's fp32 outputs — stated tolerance for bf16 operands: |d policy| <= 3e-2,
+    |d value| <= 5e-2 * max(1, |v|)."""
+    specs, nb = _positions(w, h, n)
+    sd = make_cnn_state_dict(3, blocks)
+    g = np.load(GOLD / f"cnn_{tag}_{w}x{h}.npz")
+    idx = np.arange(n) % nb
+    with Engine(concurrent_games=4, max_turns=120) as eng:
+        eng.load_weights(N.AR_ARCH_CNN, w, h, sd)
+        out = eng.nn_forward(pods_array(specs))
+    _check_vs_fp32(out, [g[k][idx] for k in ("policy_p1", "policy_p2", "value_p1", "value_p2")], 3e-2, 5e-2,
+                   f"cnn {tag} {w}x{h} n={n}")
+
+
+def test_unsupported_evaluator_shapes_fail_loudly():
+    sd = make_symmetric_state_dict(2, 7, 7, hidden=128)
+    with Engine(concurrent_games=4, max_turns=120) as eng:
+        with pytest.raises(RuntimeError, match="hidden_dim"):
+            eng.load_weights(N.AR_ARCH_SYMMETRIC, 7, 7, sd)
+        with pytest.raises(RuntimeError, match="stem.weight"):
+            eng.load_weights(N.AR_ARCH_CNN, 7, 7, sd)
 
 
 def test_nn_forward_without_weights_fails_loudly():

@@ -7,12 +7,14 @@ import json
 from pathlib import Path
 
 import numpy as np
+import pytest
 
 from alpharat_b200 import _native as N
 from alpharat_b200.engine import search_cfg
 from alpharat_b200.games import GameSpec, make_games, pods_array
 from conftest import oracle_search, oracle_selfplay
-from nn_ref import make_mlp_state_dict, mlp_forward, random_positions
+from nn_ref import (cnn_forward, make_cnn_state_dict, make_mlp_state_dict, make_symmetric_state_dict, mlp_forward,
+                    random_positions, symmetric_forward)
 
 GOLD = Path(__file__).resolve().parent / "golden"
 
@@ -57,6 +59,29 @@ def test_mlp_restatement_matches_reference_model():
     p1, p2, v1, v2 = mlp_forward(sd, obs)
     assert np.abs(p1 - g["policy_p1"]).max() <= 1e-5 and np.abs(p2 - g["policy_p2"]).max() <= 1e-5
     assert np.abs(v1 - g["value_p1"]).max() <= 1e-5 and np.abs(v2 - g["value_p2"]).max() <= 1e-5
+
+
+def _golden_obs(oracle, w, h):
+    if (w, h) == (7, 7):
+        return np.load(GOLD / "flat_builder_7x7.npz")["obs"]
+    pods = pods_array(random_positions(40, w, h, seed=321))
+    obs = np.zeros((40, 7 * w * h + 6), np.float32)
+    oracle.orc_encode(pods, 40, obs.ctypes.data_as(C.POINTER(C.c_float)))
+    return obs
+
+
+@pytest.mark.parametrize("w,h", [(7, 7), (5, 5)])
+def test_symmetric_and_cnn_restatements_match_reference_models(oracle, w, h):
+    """nn_ref.symmetric_forward / cnn_forward == SymmetricMLP.predict / PyRatCNN.predict of the real
+    reference (goldens written by tests/golden/make_golden.py), same 1e-5 bar as export_onnx --verify."""
+    obs = _golden_obs(oracle, w, h)
+    cases = [(f"symmetric_{w}x{h}.npz", symmetric_forward(make_symmetric_state_dict(2, w, h), obs, w, h))]
+    for tag, blocks in (("gpool", ("res", "res", "gpool")), ("res", ("res",))):
+        cases.append((f"cnn_{tag}_{w}x{h}.npz", cnn_forward(make_cnn_state_dict(3, blocks), obs, w, h)))
+    for name, out in cases:
+        g = np.load(GOLD / name)
+        for a, k in zip(out, ("policy_p1", "policy_p2", "value_p1", "value_p2")):
+            assert np.abs(a - g[k]).max() <= 1e-5, (name, k)
 
 
 def test_make_unmake_roundtrip(oracle):
