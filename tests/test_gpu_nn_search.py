@@ -22,7 +22,8 @@ from alpharat_b200 import _native as N
 from alpharat_b200.engine import Engine, search_cfg
 from alpharat_b200.games import make_games, pods_array
 from conftest import EVAL_CB, oracle_search, oracle_selfplay
-from nn_ref import make_mlp_state_dict, mlp_forward, random_positions
+from nn_ref import (make_cnn_state_dict, make_mlp_state_dict, make_symmetric_state_dict, mlp_forward,
+                    random_positions)
 from test_gpu_parity_uniform import assert_result_equal, compare_selfplay
 
 pytestmark = pytest.mark.gpu
@@ -78,6 +79,26 @@ def test_nn_selfplay_bit_exact_with_shared_evaluator(oracle):
         cpu = oracle_selfplay(oracle, pods, cfg, seeds, n_threads=1, eval_cb=gpu_eval_callback(eng))
     compare_selfplay(gpu, cpu, n)
     assert gpu[3].total_nn_evals > 0 and gpu[3].kernel_launches > 2
+
+
+@pytest.mark.parametrize("arch,make_sd", [
+    (N.AR_ARCH_SYMMETRIC, lambda: make_symmetric_state_dict(2, 7, 7)),
+    (N.AR_ARCH_CNN, lambda: make_cnn_state_dict(3, ("res", "res", "gpool"))),
+])
+def test_nn_selfplay_bit_exact_symmetric_and_cnn(oracle, arch, make_sd):
+    """Config 4: 7x7_rust_strong search parameters (c_puct 0.512, force_k 0.025, fpu 0.479) with the
+    SymmetricMLP / CNN-gpool evaluators; oracle driven by the same device evaluator => bit-exact."""
+    n = 5
+    specs = make_games(n, width=7, height=7, cheese_count=10, max_turns=20, first_index=900)
+    pods = pods_array(specs)
+    cfg = search_cfg(simulations=160, batch_size=16, c_puct=0.512, fpu_reduction=0.479, force_k=0.025)
+    seeds = [77 + i for i in range(n)]
+    with Engine(concurrent_games=4, max_turns=20, max_batch_size=16, max_simulations=160, pool_nodes=8192) as eng:
+        eng.load_weights(arch, 7, 7, make_sd())
+        gpu = eng.selfplay(pods, cfg, seeds)
+        cpu = oracle_selfplay(oracle, pods, cfg, seeds, n_threads=1, eval_cb=gpu_eval_callback(eng))
+    compare_selfplay(gpu, cpu, n)
+    assert gpu[3].total_nn_evals > 0
 
 
 def test_nn_search_within_tolerance_of_fp32_reference(oracle):
