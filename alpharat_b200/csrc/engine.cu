@@ -139,7 +139,7 @@ __device__ __forceinline__ void load_game(const ar_game_pod* pod, WarpCtx& cx, G
 // (play_game, selfplay.rs:515-598).  search_only: one fresh-tree search per "game"
 // (rust_mcts_search, mcts/bindings.rs:228-304).
 #ifndef AR_MIN_BLOCKS
-#define AR_MIN_BLOCKS 8
+#define AR_MIN_BLOCKS 7
 #endif
 __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(RunParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
