@@ -53,16 +53,6 @@ struct RunParams {
   ar_progress* progress;  // mapped pinned host memory (may be null)
 };
 
-__host__ __device__ inline size_t warp_smem_bytes(uint32_t max_depth, uint32_t batch_cap) {
-  size_t b = (size_t)batch_cap * sizeof(PendLevel);      // parked split levels
-  b += (size_t)batch_cap * sizeof(GPack);                // leaf states
-  b += (size_t)(batch_cap + 1) * sizeof(ChildEnt);       // parked (a1,a2) cells
-  b += (size_t)batch_cap * sizeof(TpEntry);              // batch entries
-  b += 256;                                              // maze cost table (64 cells x 4)
-  b += (size_t)max_depth * sizeof(uint32_t);             // current DFS path
-  return (b + 15) & ~(size_t)15;
-}
-
 // Optional phase timers (-DAR_PHASE_TIMING): cycles per warp in gather / backup / advance.
 #ifdef AR_PHASE_TIMING
 #define AR_T0() long long _t0 = clock64()
@@ -93,9 +83,9 @@ __device__ __forceinline__ void simulate_batch_uniform(WarpCtx& cx, const Search
   if (cx.error) return;
   AR_T1(0);
   for (int e = 0; e < n_tp; ++e) {
-    uint8_t kind = cx.tp[e].kind;
+    uint8_t kind = cx.tp()[e].kind;
     if (kind == 1) term += 1; else nn += 1;
-    if (kind == 0 && cx.tp[e].node == 0 && sp.noise_epsilon > 0.0f) apply_root_noise(cx, sp, rng, lane);
+    if (kind == 0 && cx.tp()[e].node == 0 && sp.noise_epsilon > 0.0f) apply_root_noise(cx, sp, rng, lane);
     backup_entry(cx, e, 0.0f, 0.0f, nullptr, nullptr, lane);
   }
   AR_T1(1);
@@ -122,8 +112,19 @@ __device__ __forceinline__ void load_game(const ar_game_pod* pod, WarpCtx& cx, G
   turn = pod->turn;
   __syncwarp();
   for (int i = lane; i < 64; i += 32)  // 64 cells x 4 directions = 64 words
-    reinterpret_cast<uint32_t*>(cx.maze)[i] =
+    reinterpret_cast<uint32_t*>(cx.maze())[i] =
         (i < cx.cells) ? reinterpret_cast<const uint32_t*>(pod->move_cost)[i] : 0u;
+  uint16_t* tbl = const_cast<uint16_t*>(cx.steptbl());
+  for (int i = lane; i < 64 * 8; i += 32) {  // move table: target cell | mud cost << 8
+    const int c = i >> 3, a = i & 7;
+    uint32_t e = (uint32_t)c;
+    if (a < 4 && c < cx.cells) {
+      const int cost = pod->move_cost[c * 4 + a];
+      const int mag = (a & 1) ? 1 : cx.w;
+      if (cost) e = (uint32_t)(c + ((a & 2) ? -mag : mag)) | ((uint32_t)(cost >= 2 ? cost : 0) << 8);
+    }
+    tbl[i] = (uint16_t)e;
+  }
   g.cheese = *reinterpret_cast<const uint64_t*>(pod->cheese);
   g.p1 = pod->p1_y * pod->width + pod->p1_x;
   g.p2 = pod->p2_y * pod->width + pod->p2_x;
@@ -143,26 +144,20 @@ __device__ __forceinline__ void load_game(const ar_game_pod* pod, WarpCtx& cx, G
 #endif
 __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(RunParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int lane = threadIdx.x & 31;
+  int lane = threadIdx.x & 31;
+  asm volatile("" : "+r"(lane));
   const int wib = threadIdx.x >> 5;
   const int slot = blockIdx.x * 4 + wib;
   if (slot >= p.n_slots) return;
 
   uint8_t* base = smem + (size_t)wib * warp_smem_bytes(p.max_depth, p.batch_cap);
   WarpCtx cx;
-  cx.pend = reinterpret_cast<PendLevel*>(base);
-  cx.tp_state = reinterpret_cast<GPack*>(cx.pend + p.batch_cap);
-  cx.cstack = reinterpret_cast<ChildEnt*>(cx.tp_state + p.batch_cap);
-  cx.tp = reinterpret_cast<TpEntry*>(cx.cstack + (p.batch_cap + 1));
-  cx.maze = reinterpret_cast<uint8_t*>(cx.tp + p.batch_cap);
-  cx.path = reinterpret_cast<uint32_t*>(cx.maze + 256);
-  cx.pool = p.pools + (size_t)slot * p.pool_nodes;
+  cx.bind(base, p.pools + (size_t)slot * p.pool_nodes, lane, p.max_depth, p.batch_cap);
   cx.path_buf = p.path_bufs + (size_t)slot * p.batch_cap * p.path_stride;
   cx.remap = p.remaps + (size_t)slot * p.pool_nodes;
   cx.coll_table = p.coll_table;
   cx.pool_nodes = p.pool_nodes;
   cx.path_stride = p.path_stride;
-  cx.max_depth = p.max_depth;
   cx.epoch = 1;
   cx.path_nodes = 0;
   cx.new_nodes = 0;
@@ -237,7 +232,7 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(Ru
       uint32_t rmeta = cx.pool[0].s[LANE_LINKS].y;
       int i = action_to_idx(meta_m1(rmeta), a1), j = action_to_idx(meta_m2(rmeta), a2);
       uint32_t child = reinterpret_cast<const uint32_t*>(&cx.pool[0].s[LANE_CHILD])[i * 5 + j];
-      game_step(g, a1, a2, cx.maze, cx.w);
+      game_step(g, a1, a2, cx.steptbl());
       turn += 1;
       __syncwarp();
       AR_T0();
@@ -335,7 +330,8 @@ __global__ void nn_init_slots_kernel(SlotState* slots, int n) {
 
 __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p, NnParams q) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int lane = threadIdx.x & 31;
+  int lane = threadIdx.x & 31;
+  asm volatile("" : "+r"(lane));
   const int wib = threadIdx.x >> 5;
   const int slot = blockIdx.x * 4 + wib;
   if (slot >= p.n_slots) return;
@@ -344,19 +340,12 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
 
   uint8_t* base = smem + (size_t)wib * warp_smem_bytes(p.max_depth, p.batch_cap);
   WarpCtx cx;
-  cx.pend = reinterpret_cast<PendLevel*>(base);
-  cx.tp_state = reinterpret_cast<GPack*>(cx.pend + p.batch_cap);
-  cx.cstack = reinterpret_cast<ChildEnt*>(cx.tp_state + p.batch_cap);
-  cx.tp = reinterpret_cast<TpEntry*>(cx.cstack + (p.batch_cap + 1));
-  cx.maze = reinterpret_cast<uint8_t*>(cx.tp + p.batch_cap);
-  cx.path = reinterpret_cast<uint32_t*>(cx.maze + 256);
-  cx.pool = p.pools + (size_t)slot * p.pool_nodes;
+  cx.bind(base, p.pools + (size_t)slot * p.pool_nodes, lane, p.max_depth, p.batch_cap);
   cx.path_buf = p.path_bufs + (size_t)slot * p.batch_cap * p.path_stride;
   cx.remap = p.remaps + (size_t)slot * p.pool_nodes;
   cx.coll_table = p.coll_table;
   cx.pool_nodes = p.pool_nodes;
   cx.path_stride = p.path_stride;
-  cx.max_depth = p.max_depth;
   const SearchParams sp = p.sp;
 
   SlotState st = *sp_g;
@@ -404,15 +393,15 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
     if (st.phase == PH_WAIT_EVAL) {
       // ---- populate + backup in to_process order (search.rs:1028-1058)
       const int n_tp = (int)st.n_tp;
-      for (int e = lane; e < n_tp; e += 32) cx.tp[e] = tp_g[e];
+      for (int e = lane; e < n_tp; e += 32) cx.tp()[e] = tp_g[e];
       __syncwarp();
       uint32_t row = st.row_base, nn_b = 0, term_b = 0;
       for (int e = 0; e < n_tp; ++e) {
-        if (cx.tp[e].kind == 0) {
+        if (cx.tp()[e].kind == 0) {
           const float* o = q.nn_out + (size_t)row * 12;
           row += 1;
           nn_b += 1;
-          if (cx.tp[e].node == 0 && sp.noise_epsilon > 0.0f) {
+          if (cx.tp()[e].node == 0 && sp.noise_epsilon > 0.0f) {
             // populate first, then noise, then backup (search.rs:1034-1052)
             backup_entry(cx, e, o[10], o[11], o, o + 5, lane, /*populate_only=*/true);
             apply_root_noise(cx, sp, rng, lane);
@@ -468,7 +457,7 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
           uint32_t rmeta = cx.pool[0].s[LANE_LINKS].y;
           int i = action_to_idx(meta_m1(rmeta), a1), j = action_to_idx(meta_m2(rmeta), a2);
           uint32_t child = reinterpret_cast<const uint32_t*>(&cx.pool[0].s[LANE_CHILD])[i * 5 + j];
-          game_step(g, a1, a2, cx.maze, cx.w);
+          game_step(g, a1, a2, cx.steptbl());
           turn += 1;
           __syncwarp();
           if (child != 0) {
@@ -525,8 +514,8 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
       }
       if (cx.error) break;
       __syncwarp();
-      uint32_t evmask = __ballot_sync(FULL, lane < n_tp && cx.tp[lane].kind == 0);
-      uint32_t evmask_hi = n_tp > 32 ? __ballot_sync(FULL, lane + 32 < n_tp && cx.tp[lane + 32].kind == 0) : 0u;
+      uint32_t evmask = __ballot_sync(FULL, lane < n_tp && cx.tp()[lane].kind == 0);
+      uint32_t evmask_hi = n_tp > 32 ? __ballot_sync(FULL, lane + 32 < n_tp && cx.tp()[lane + 32].kind == 0) : 0u;
       const uint32_t n_eval = __popc(evmask) + __popc(evmask_hi);
       st.n_tp = (uint32_t)n_tp;
       if (n_eval == 0) {
@@ -543,13 +532,13 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
       if (rb + n_eval > q.max_rows) { cx.error = AR_ERR_POOL_OVERFLOW; break; }
       st.row_base = rb;
       for (int e = lane; e < n_tp; e += 32) {
-        TpEntry te = cx.tp[e];
+        TpEntry te = cx.tp()[e];
         tp_g[e] = te;
         if (te.kind == 0) {
           uint32_t m = e < 32 ? (evmask & ((1u << e) - 1u)) : evmask;
           uint32_t mh = e < 32 ? 0u : (evmask_hi & ((1u << (e - 32)) - 1u));
           uint32_t r = rb + __popc(m) + __popc(mh);
-          GPack gp = cx.tp_state[e];
+          GPack gp = cx.tp_state()[e];
           EvalRow er;
           er.cheese = gp.cheese;
           er.pos = gp.pos;
