@@ -86,7 +86,7 @@ __device__ __forceinline__ void simulate_batch_uniform(WarpCtx& cx, const Search
     uint8_t kind = cx.tp()[e].kind;
     if (kind == 1) term += 1; else nn += 1;
     if (kind == 0 && cx.tp()[e].node == 0 && sp.noise_epsilon > 0.0f) apply_root_noise(cx, sp, rng, lane);
-    backup_entry(cx, e, 0.0f, 0.0f, nullptr, nullptr, lane);
+    backup_entry<true>(cx, e, 0.0f, 0.0f, nullptr, nullptr, lane);
   }
   AR_T1(1);
 }
