@@ -40,6 +40,10 @@ class SplitMix64:
     def below(self, n: int) -> int:
         return self.next() % n
 
+    def random(self) -> float:
+        """Uniform in [0, 1) with 53 bits."""
+        return (self.next() >> 11) * (1.0 / (1 << 53))
+
 
 @dataclass
 class GameSpec:
@@ -171,6 +175,75 @@ def random_cheese(width: int, height: int, count: int, symmetric: bool, rng: Spl
     return chosen
 
 
+def random_maze(width: int, height: int, wall_density: float, mud_density: float, mud_range: int,
+                symmetric: bool, rng: SplitMix64):
+    """Connected random maze: (walls, mud) as `GameSpec` edge lists.
+
+    Same knobs as the engine's `MazeParams` (bindings.rs:509-519: wall_density, mud_density,
+    mud_range, connected=True, symmetric).  The engine's own generator is third-party code that is
+    not available offline, so this is this module's documented procedure, not a bit-for-bit twin:
+      1. every inner edge (orbit of the 180-degree rotation when `symmetric`) is walled with
+         probability `wall_density`, visited in row-major order (horizontal edge before vertical);
+      2. while the maze is disconnected, the walled orbits that separate two components are listed
+         in the same order and one of them, drawn uniformly, is opened;
+      3. every open orbit gets mud with probability `mud_density`, cost uniform in [2, mud_range].
+    """
+    def mirror(c):
+        return (width - 1 - c[0], height - 1 - c[1])
+
+    orbits, seen = [], set()
+    for y in range(height):
+        for x in range(width):
+            for nx, ny in ((x + 1, y), (x, y + 1)):
+                if nx >= width or ny >= height:
+                    continue
+                e = ((x, y), (nx, ny))
+                if e in seen:
+                    continue
+                orbit = [e]
+                if symmetric:
+                    m = (mirror(e[1]), mirror(e[0]))  # keeps the (lower, upper) orientation
+                    if m != e:
+                        orbit.append(m)
+                seen.update(orbit)
+                orbits.append(orbit)
+    walled = [rng.random() < wall_density for _ in orbits]
+
+    def components():
+        parent = list(range(width * height))
+
+        def find(a):
+            while parent[a] != a:
+                parent[a] = parent[parent[a]]
+                a = parent[a]
+            return a
+
+        for o, w in zip(orbits, walled):
+            if not w:
+                for a, b in o:
+                    ra, rb = find(a[1] * width + a[0]), find(b[1] * width + b[0])
+                    if ra != rb:
+                        parent[ra] = rb
+        return find
+
+    while True:
+        find = components()
+        roots = {find(c) for c in range(width * height)}
+        if len(roots) == 1:
+            break
+        cand = [i for i, (o, w) in enumerate(zip(orbits, walled)) if w and any(
+            find(a[1] * width + a[0]) != find(b[1] * width + b[0]) for a, b in o)]
+        walled[cand[rng.below(len(cand))]] = False
+    walls, mud = [], []
+    for o, w in zip(orbits, walled):
+        if w:
+            walls.extend(o)
+        elif mud_density > 0.0 and rng.random() < mud_density:
+            cost = 2 + (rng.below(mud_range - 1) if mud_range > 2 else 0)
+            mud.extend((a, b, cost) for a, b in o)
+    return walls, mud
+
+
 def make_games(
     num_games: int,
     *,
@@ -181,23 +254,43 @@ def make_games(
     cheese_symmetric: bool = True,
     maze_type: str = "open",
     positions: str = "corners",
+    wall_density: float = 0.7,
+    mud_density: float = 0.1,
+    maze_symmetric: bool = True,
     first_index: int = 0,
 ) -> list[GameSpec]:
-    """Generator behind `cuda_self_play` (same axes as `make_games`, bindings.rs:489-533).
-
-    Only `maze_type="open"` / `positions="corners"` are generated here; walls and mud are
-    accepted through explicit `GameSpec`s (`games=` argument of `cuda_self_play`).
-    """
-    if maze_type != "open":
-        raise ValueError(f"maze_type={maze_type!r}: only 'open' is generated; pass games= explicitly")
-    if positions != "corners":
-        raise ValueError(f"positions={positions!r}: only 'corners' is generated; pass games= explicitly")
-    p1, p2 = (0, 0), (width - 1, height - 1)
+    """Generator behind `cuda_self_play` (same axes as `make_games`, bindings.rs:489-533):
+    maze_type open / classic (wall 0.7, mud 0.1, symmetric) / random; positions corners / random
+    (P2 is the 180-degree mirror of P1 when the cheese is symmetric); random cheese.
+    One SplitMix64 stream per game, keyed by the game index."""
+    if maze_type not in ("open", "classic", "random"):
+        raise ValueError(f"unknown maze_type: {maze_type!r}")
+    if positions not in ("corners", "random"):
+        raise ValueError(f"unknown positions: {positions!r}")
     out = []
     for i in range(num_games):
         rng = SplitMix64(first_index + i)
+        walls, mud = [], []
+        if maze_type == "classic":
+            walls, mud = random_maze(width, height, 0.7, 0.1, 3, True, rng)
+        elif maze_type == "random":
+            walls, mud = random_maze(width, height, wall_density, mud_density, 3 if mud_density > 0.0 else 2,
+                                     maze_symmetric, rng)
+        if positions == "corners":
+            p1, p2 = (0, 0), (width - 1, height - 1)
+        else:
+            while True:
+                c = rng.below(width * height)
+                p1 = (c % width, c // width)
+                if cheese_symmetric:
+                    p2 = (width - 1 - p1[0], height - 1 - p1[1])
+                else:
+                    c2 = rng.below(width * height)
+                    p2 = (c2 % width, c2 // width)
+                if p1 != p2:
+                    break
         cheese = random_cheese(width, height, cheese_count, cheese_symmetric, rng, (p1, p2))
-        out.append(GameSpec(width, height, max_turns, p1, p2, cheese))
+        out.append(GameSpec(width, height, max_turns, p1, p2, cheese, walls=walls, mud=mud))
     return out
 
 

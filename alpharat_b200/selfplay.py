@@ -142,7 +142,8 @@ def cuda_self_play(
         raise NotImplementedError("cache_size > 0 (NN eval cache) is not implemented in backend cuda")
     specs = list(games) if games is not None else make_games(
         num_games, width=width, height=height, cheese_count=cheese_count, max_turns=max_turns,
-        cheese_symmetric=cheese_symmetric, maze_type=maze_type, positions=positions)
+        cheese_symmetric=cheese_symmetric, maze_type=maze_type, positions=positions, wall_density=wall_density,
+        mud_density=mud_density, maze_symmetric=maze_symmetric)
     if games is not None and len(specs) != num_games:
         raise ValueError("len(games) != num_games")
     cfg = search_cfg(simulations=simulations, batch_size=batch_size, c_puct=c_puct,

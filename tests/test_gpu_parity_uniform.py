@@ -83,6 +83,20 @@ def test_selfplay_7x7_tuned(oracle):
     compare_selfplay(gpu, cpu, n)
 
 
+def test_selfplay_classic_mazes_with_walls_and_mud(oracle):
+    """walls, mud timers (the [4,4,4,4,4] stuck outcome), random starts, non-square board."""
+    n = 48
+    specs = make_games(n, width=7, height=5, cheese_count=6, max_turns=40, maze_type="classic", positions="random",
+                       first_index=4000)
+    pods = pods_array(specs)
+    cfg = search_cfg(simulations=300, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103)
+    seeds = [31 * i + 5 for i in range(n)]
+    with Engine(concurrent_games=32, max_turns=40, max_batch_size=16, max_simulations=300) as eng:
+        gpu = eng.selfplay(pods, cfg, seeds)
+    cpu = oracle_selfplay(oracle, pods, cfg, seeds)
+    compare_selfplay(gpu, cpu, n)
+
+
 def test_search_batch_matches_oracle(oracle):
     specs = make_games(32, width=5, height=5, cheese_count=5, max_turns=30)
     specs += [

@@ -15,7 +15,7 @@ import alpharat_b200 as ab
 from alpharat_b200 import _native as N
 from alpharat_b200.bundle import BUNDLE_KEYS, write_bundles
 from alpharat_b200.engine import search_cfg
-from alpharat_b200.games import GameSpec, make_games, maze_array, pods_array
+from alpharat_b200.games import move_cost_table, GameSpec, make_games, maze_array, pods_array
 from conftest import oracle_selfplay
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -95,7 +95,36 @@ def test_game_generator_properties():
     shifted = make_games(3, width=7, height=7, cheese_count=10, max_turns=50, first_index=5)
     assert shifted[0].cheese == specs[5].cheese
     with pytest.raises(ValueError):
-        make_games(1, width=5, height=5, cheese_count=5, max_turns=30, maze_type="random")
+        make_games(1, width=5, height=5, cheese_count=5, max_turns=30, maze_type="hexagonal")
+
+
+@pytest.mark.parametrize("maze_type,sym", [("classic", True), ("random", True), ("random", False)])
+def test_random_maze_generator_is_connected_symmetric_and_reproducible(maze_type, sym):
+    """Same knobs as make_games (bindings.rs:489-533): maze_type classic/random, random positions."""
+    kw = dict(width=7, height=5, cheese_count=6, max_turns=40, maze_type=maze_type, positions="random",
+              wall_density=0.6, mud_density=0.25, maze_symmetric=sym)
+    specs = make_games(40, **kw)
+    assert [(s.walls, s.mud, s.p1, s.p2) for s in specs] == [(s.walls, s.mud, s.p1, s.p2) for s in make_games(40, **kw)]
+    delta = {0: (0, 1), 1: (1, 0), 2: (0, -1), 3: (-1, 0)}
+    n_walls = n_mud = 0
+    for s in specs:
+        mc = move_cost_table(7, 5, s.walls, s.mud).reshape(5, 7, 4)
+        seen, todo = {s.p1}, [s.p1]
+        while todo:  # every cell reachable: MazeParams.connected
+            x, y = todo.pop()
+            for d, (dx, dy) in delta.items():
+                if mc[y, x, d] and (x + dx, y + dy) not in seen:
+                    seen.add((x + dx, y + dy))
+                    todo.append((x + dx, y + dy))
+        assert len(seen) == 35
+        if sym or maze_type == "classic":
+            assert (mc[::-1, ::-1, :][:, :, [2, 3, 0, 1]] == mc).all()
+        assert set(np.unique(mc)) <= {0, 1, 2, 3}
+        assert s.p1 != s.p2 and s.p2 == (6 - s.p1[0], 4 - s.p1[1])
+        assert s.p1 not in s.cheese and s.p2 not in s.cheese
+        n_walls += len(s.walls)
+        n_mud += len(s.mud)
+    assert n_walls > 0 and n_mud > 0
 
 
 def test_maze_array_and_pod_packing():
