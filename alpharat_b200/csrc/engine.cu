@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(Ru
       turn += 1;
       __syncwarp();
       AR_T0();
+      if (game_over(g, turn, cx.max_turns)) break;  // the tree of a finished game is dropped
       if (child != 0) {
         compact_subtree(cx, child, lane);
         AR_T1(2);
@@ -291,7 +292,10 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(Ru
 // steps to know when every game is finished.  Replaces MuxBackend's cross-game batching
 // (crates/alpharat-sampling/src/backends/mux.rs:170-289).
 // =========================================================================================
-enum SlotPhase : uint32_t { PH_IDLE = 0, PH_GATHER = 1, PH_WAIT_EVAL = 2, PH_DONE = 3 };
+enum SlotPhase : uint32_t { PH_IDLE = 0, PH_GATHER = 1, PH_WAIT_EVAL = 2, PH_DONE = 3, PH_COMPACT = 4 };
+// Loop iterations of the tree compaction (32 nodes marked or 4 records moved each) a slot may spend
+// in one step: about the cost of gathering one batch.
+constexpr int COMPACT_ITERS_PER_STEP = 48;
 
 struct SlotState {
   GPack g;
@@ -304,7 +308,8 @@ struct SlotState {
   uint32_t n_tp, row_base;
   uint32_t phase, error;
   uint32_t path_nodes, new_nodes;
-  uint32_t pad[2];
+  CompactState comp;
+  uint32_t pad[1];
 };
 
 struct NnParams {
@@ -390,6 +395,12 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
       st.phase = PH_GATHER;
       if (!p.search_only && game_over(g, turn, cx.max_turns)) st.remaining = 0;  // empty game
     }
+    if (st.phase == PH_COMPACT) {
+      int budget = COMPACT_ITERS_PER_STEP;
+      if (!compact_step(cx, st.comp, lane, budget)) break;
+      st.phase = PH_GATHER;
+      if (budget < COMPACT_ITERS_PER_STEP / 2) break;  // gather in the next step
+    }
     if (st.phase == PH_WAIT_EVAL) {
       // ---- populate + backup in to_process order (search.rs:1028-1058)
       const int n_tp = (int)st.n_tp;
@@ -460,13 +471,16 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
           game_step(g, a1, a2, cx.steptbl());
           turn += 1;
           __syncwarp();
-          if (child != 0) {
-            compact_subtree(cx, child, lane);
-          } else {
-            cx.epoch += 1;
-            init_root(cx, g, lane);
-          }
           moved = true;
+          if (!game_over(g, turn, cx.max_turns)) {  // the tree of a finished game is dropped
+            if (child != 0) {
+              st.comp = compact_begin(cx, child);  // advance_root, spread over the next steps
+              st.phase = PH_COMPACT;
+            } else {
+              cx.epoch += 1;
+              init_root(cx, g, lane);  // reinit, tree.rs:298-302
+            }
+          }
         }
         if (game_over(g, turn, cx.max_turns)) {
           if (lane == 0) {
@@ -495,8 +509,8 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
         }
         st.remaining = sp.n_sims;
         st.nn = st.term = st.coll = 0;
-        // the step is bulk-synchronous: a slot that just compacted its tree gathers next step,
-        // so the step's critical path is max(backup + advance, backup + gather), not their sum
+        // the step is bulk-synchronous: a slot that just moved starts its next search (or the
+        // compaction of its tree) in the next step, so that the step's critical path stays short
         if (moved) break;
       }
       // ---- gather one batch (simulate_batch up to the evaluator, search.rs:961-1023)
@@ -574,6 +588,20 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
   }
 }
 
+// Games end long before max_turns on average: pack the records that exist (one warp per game)
+// so that the device-to-host copy moves only those.
+__global__ void compact_positions_kernel(const ar_position_record* __restrict__ src, int stride,
+                                         const uint32_t* __restrict__ offsets, int n,
+                                         ar_position_record* __restrict__ dst) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (g >= n) return;
+  const uint32_t b = offsets[g], e = offsets[g + 1];
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(src + (size_t)g * stride);
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst + b);
+  const uint32_t words = (e - b) * (uint32_t)(sizeof(ar_position_record) / 4);
+  for (uint32_t i = lane; i < words; i += 32) d[i] = s[i];
+}
+
 }  // namespace ar
 
 // =========================================================================================
@@ -603,6 +631,11 @@ struct ar_engine {
   ar_position_record* d_positions = nullptr;
   ar_search_result* d_search = nullptr;
   int cap_games = 0, cap_stride = 0, cap_search = 0;
+  ar_position_record* d_dense = nullptr;   // packed records for the download
+  ar_position_record* h_dense = nullptr;   // pinned staging
+  uint32_t* d_offsets = nullptr;
+  size_t cap_dense = 0;
+  int cap_offsets = 0;
   int n_resident = 0, resident_stride = 0;
   std::vector<ar_game_pod> h_games;  // kept for cheese-outcome attribution
   unsigned int* d_next = nullptr;
@@ -831,6 +864,8 @@ void ar_engine_destroy(ar_engine* e) {
   cudaFree(e->d_games); cudaFree(e->d_seeds); cudaFree(e->d_summaries); cudaFree(e->d_positions);
   cudaFree(e->d_search); cudaFree(e->d_next); cudaFree(e->d_counters); cudaFree(e->d_error);
   cudaFree(e->d_rows); cudaFree(e->d_nn_out);
+  cudaFree(e->d_dense); cudaFree(e->d_offsets);
+  if (e->h_dense) cudaFreeHost(e->h_dense);
   cudaFree(e->d_slots); cudaFree(e->d_tp_store); cudaFree(e->d_queue); cudaFree(e->d_queue_out); cudaFree(e->d_n_rows);
   delete e->eval;
   if (e->h_progress) cudaFreeHost(e->h_progress);
@@ -1139,11 +1174,37 @@ ar_status ar_selfplay_download(ar_engine* e, ar_game_summary* summaries, ar_posi
       e->err = "positions_stride smaller than a game's length";
       return AR_ERR_INVALID_ARG;
     }
-  int copy_w = std::min(positions_stride, e->resident_stride);
-  CK(cudaMemcpy2D(positions, (size_t)positions_stride * sizeof(ar_position_record), e->d_positions,
-                  (size_t)e->resident_stride * sizeof(ar_position_record),
-                  (size_t)copy_w * sizeof(ar_position_record), n, cudaMemcpyDeviceToHost));
-  e->d2h += (uint64_t)n * (sizeof(ar_game_summary) + (size_t)copy_w * sizeof(ar_position_record));
+  // pack on device, one bulk copy into pinned staging, scatter into the caller's strided array
+  std::vector<uint32_t> off((size_t)n + 1, 0);
+  for (int i = 0; i < n; ++i) off[i + 1] = off[i] + summaries[i].n_positions;
+  const size_t total = off[n];
+  if (n + 1 > e->cap_offsets) {
+    cudaFree(e->d_offsets);
+    e->d_offsets = nullptr;
+    CK(cudaMalloc(&e->d_offsets, ((size_t)n + 1) * sizeof(uint32_t)));
+    e->cap_offsets = n + 1;
+  }
+  if (total > e->cap_dense) {
+    cudaFree(e->d_dense);
+    if (e->h_dense) cudaFreeHost(e->h_dense);
+    e->d_dense = nullptr; e->h_dense = nullptr;
+    CK(cudaMalloc(&e->d_dense, total * sizeof(ar_position_record)));
+    CK(cudaHostAlloc(&e->h_dense, total * sizeof(ar_position_record), cudaHostAllocDefault));
+    e->cap_dense = total;
+  }
+  if (total > 0) {
+    CK(cudaMemcpyAsync(e->d_offsets, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    compact_positions_kernel<<<(n + 7) / 8, 256, 0, e->stream>>>(e->d_positions, e->resident_stride, e->d_offsets, n,
+                                                                 e->d_dense);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->h_dense, e->d_dense, total * sizeof(ar_position_record), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < n; ++i)
+      memcpy(positions + (size_t)i * positions_stride, e->h_dense + off[i],
+             (size_t)summaries[i].n_positions * sizeof(ar_position_record));
+  }
+  e->launches += 1;
+  e->d2h += (uint64_t)n * sizeof(ar_game_summary) + total * sizeof(ar_position_record);
   for (int i = 0; i < n; ++i)
     attribute_cheese(e->h_games[i], summaries[i], positions + (size_t)i * positions_stride);
   return AR_OK;

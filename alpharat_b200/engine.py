@@ -45,6 +45,7 @@ class Engine:
             raise _STATUS_EXC.get(st, RuntimeError)(f"ar_engine_create failed ({st}): {msg.decode() if msg else ''}")
         self._h = handle
         self.cfg = cfg
+        self.has_evaluator = False
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -82,6 +83,7 @@ class Engine:
                 descs[i].shape[d] = a.shape[d] if d < a.ndim else 1
         self._check(self._lib.ar_engine_load_weights(self._h, arch, width, height, descs, len(tensors)),
                     "ar_engine_load_weights")
+        self.has_evaluator = arch != N.AR_ARCH_UNIFORM
 
     # --- search ----------------------------------------------------------------------------
     def search_batch(self, pods, cfg: N.SearchCfg, seeds: Sequence[int]):
@@ -91,6 +93,16 @@ class Engine:
         self._check(self._lib.ar_search_batch(self._h, pods, n, C.byref(cfg), sd, out), "ar_search_batch")
         return out
 
+    @staticmethod
+    def _record_array(count: int):
+        """`PositionRecord[count]` over lazily mapped (untouched, unzeroed) memory: only the rows a game
+        really played are ever written, so the pages of the unused tail of each stride are never faulted
+        in (a zero-filled ctypes array of the bench's 65536 x 50 records costs 0.6 s on its own)."""
+        if count * C.sizeof(N.PositionRecord) < (1 << 20):
+            return (N.PositionRecord * count)()
+        buf = np.empty(count * C.sizeof(N.PositionRecord), dtype=np.uint8)
+        return (N.PositionRecord * count).from_buffer(buf)
+
     # --- self-play ---------------------------------------------------------------------------
     def selfplay(self, pods, cfg: N.SearchCfg, seeds: Sequence[int], *, stride: int | None = None,
                  progress: N.Progress | None = None):
@@ -98,7 +110,7 @@ class Engine:
         if stride is None:
             stride = max([p.max_turns for p in pods] + [1])
         summaries = (N.GameSummary * max(n, 1))()
-        positions = (N.PositionRecord * max(n * stride, 1))()
+        positions = self._record_array(max(n * stride, 1))
         stats = N.Stats()
         sd = (C.c_uint64 * max(n, 1))(*[int(s) & ((1 << 64) - 1) for s in seeds])
         pr = C.byref(progress) if progress is not None else None
@@ -119,7 +131,7 @@ class Engine:
 
     def selfplay_download(self, n: int, stride: int):
         summaries = (N.GameSummary * max(n, 1))()
-        positions = (N.PositionRecord * max(n * stride, 1))()
+        positions = self._record_array(max(n * stride, 1))
         self._check(self._lib.ar_selfplay_download(self._h, summaries, positions, stride), "ar_selfplay_download")
         return summaries, positions
 
