@@ -651,6 +651,8 @@ struct ar_engine {
   EvalRow* d_rows = nullptr;
   float* d_nn_out = nullptr;
   int cap_rows = 0;
+  uint16_t* d_maze_tab = nullptr;  // per-game bf16 maze channels (build_maze_table)
+  int cap_maze = 0;
   // NN-mode step state
   SlotState* d_slots = nullptr;
   TpEntry* d_tp_store = nullptr;
@@ -864,7 +866,7 @@ void ar_engine_destroy(ar_engine* e) {
   cudaFree(e->d_games); cudaFree(e->d_seeds); cudaFree(e->d_summaries); cudaFree(e->d_positions);
   cudaFree(e->d_search); cudaFree(e->d_next); cudaFree(e->d_counters); cudaFree(e->d_error);
   cudaFree(e->d_rows); cudaFree(e->d_nn_out);
-  cudaFree(e->d_dense); cudaFree(e->d_offsets);
+  cudaFree(e->d_dense); cudaFree(e->d_offsets); cudaFree(e->d_maze_tab);
   if (e->h_dense) cudaFreeHost(e->h_dense);
   cudaFree(e->d_slots); cudaFree(e->d_tp_store); cudaFree(e->d_queue); cudaFree(e->d_queue_out); cudaFree(e->d_n_rows);
   delete e->eval;
@@ -925,6 +927,18 @@ static RunParams make_params(ar_engine* e, const ar_search_cfg* cfg) {
   return p;
 }
 
+// (Re)build the evaluators' per-game maze table for the n games resident in e->d_games.
+static ar_status ensure_maze_table(ar_engine* e, int n) {
+  if (n > e->cap_maze) {
+    cudaFree(e->d_maze_tab);
+    e->d_maze_tab = nullptr;
+    CK(cudaMalloc(&e->d_maze_tab, (size_t)n * MAZE_TAB_STRIDE * sizeof(uint16_t)));
+    e->cap_maze = n;
+  }
+  CK(build_maze_table(e->d_games, n, e->d_maze_tab, e->stream));
+  return AR_OK;
+}
+
 static ar_status ensure_nn_buffers(ar_engine* e) {
   if (e->d_slots) return AR_OK;
   size_t max_rows = (size_t)e->n_slots * e->batch_cap;
@@ -949,6 +963,8 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
   const bool nn = e->arch != AR_ARCH_UNIFORM;
   if (nn) {
     ar_status s = ensure_nn_buffers(e);
+    if (s) return s;
+    s = ensure_maze_table(e, p.n_games);
     if (s) return s;
   }
   CK(cudaEventRecord(e->ev0, e->stream));
@@ -975,7 +991,8 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
         CK(cudaMemsetAsync(e->d_n_rows, 0, sizeof(uint32_t), e->stream));
         nn_step_kernel<<<blocks, 128, smem, e->stream>>>(p, q);
         CK(cudaGetLastError());
-        CK(e->eval->forward(e->d_queue, e->d_n_rows, (int)q.max_rows, p.games, e->d_queue_out, e->d_error, e->stream));
+        CK(e->eval->forward(e->d_queue, e->d_n_rows, (int)q.max_rows, p.games, e->d_maze_tab, e->d_queue_out, e->d_error,
+                            e->stream));
         e->launches += 2;
         e->nn_steps += 1;
       }
@@ -1289,7 +1306,9 @@ ar_status ar_nn_forward(ar_engine* e, const ar_game_pod* games, int32_t n, float
       return AR_ERR_INVALID_ARG;
     }
   CK(cudaMemsetAsync(e->d_error, 0, sizeof(int), e->stream));
-  CK(e->eval->forward(e->d_rows, nullptr, n, e->d_games, e->d_nn_out, e->d_error, e->stream));
+  s = ensure_maze_table(e, n);
+  if (s) return s;
+  CK(e->eval->forward(e->d_rows, nullptr, n, e->d_games, e->d_maze_tab, e->d_nn_out, e->d_error, e->stream));
   std::vector<float> out((size_t)n * 12);
   CK(cudaMemcpyAsync(out.data(), e->d_nn_out, out.size() * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
   int herr = 0;

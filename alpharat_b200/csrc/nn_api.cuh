@@ -34,12 +34,13 @@ struct MlpWeights {
 // A loaded leaf evaluator (replaces `dyn Backend`, crates/alpharat-mcts/src/backend.rs:75-82, for the
 // NN-guided mode).  forward() scores `rows` into out[row][12] = policy_p1[5], policy_p2[5], v1, v2.
 // n_rows_dev != nullptr: the row count is read on device (the self-play loop never syncs).
+// maze_tab: build_maze_table() of `games`.
 struct LeafEvaluator {
   virtual ~LeafEvaluator() {}
   virtual int load(const ar_tensor_desc* tensors, int n, int width, int height, std::string& err) = 0;
   virtual cudaError_t forward(const EvalRow* rows, const uint32_t* n_rows_dev, int n_rows_max,
-                              const ar_game_pod* games, float* out, int* error_flag,
-                              cudaStream_t stream) const = 0;
+                              const ar_game_pod* games, const uint16_t* maze_tab, float* out,
+                              int* error_flag, cudaStream_t stream) const = 0;
 };
 
 struct MlpModel : LeafEvaluator {
@@ -51,12 +52,19 @@ struct MlpModel : LeafEvaluator {
   ~MlpModel() override { release(); }
   int load(const ar_tensor_desc* tensors, int n, int width, int height, std::string& err) override;
   cudaError_t forward(const EvalRow* rows, const uint32_t* n_rows_dev, int n_rows_max,
-                      const ar_game_pod* games, float* out, int* error_flag, cudaStream_t stream) const override;
+                      const ar_game_pod* games, const uint16_t* maze_tab, float* out, int* error_flag,
+                      cudaStream_t stream) const override;
   void release();
 };
 
 LeafEvaluator* make_symmetric_evaluator();  // nn_symmetric.cu
 LeafEvaluator* make_cnn_evaluator();        // nn_cnn.cu
+
+// Per-game maze channels of the observation as bf16 (flat_encoder.rs:62-80): out[game][cell * 4 + dir],
+// 256 entries per game, zero past the board.  The maze never changes during a game, so the
+// evaluators copy these rows instead of re-deriving 4 * cells values for every leaf.
+constexpr int MAZE_TAB_STRIDE = 256;
+cudaError_t build_maze_table(const ar_game_pod* games, int n, uint16_t* out, cudaStream_t stream);
 
 cudaError_t encode_f32(const EvalRow* rows, int n, const ar_game_pod* games, int obs_dim, float* out,
                        cudaStream_t stream);

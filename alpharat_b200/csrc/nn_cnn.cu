@@ -120,8 +120,8 @@ __device__ __forceinline__ void pack16(const float v[16], uint4& lo, uint4& hi) 
 
 __global__ void __launch_bounds__(THREADS, 1)
 cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict__ n_rows_ptr, int n_rows_arg,
-                   const ar_game_pod* __restrict__ games, Params pr, float* __restrict__ out,
-                   int* __restrict__ error_flag) {
+                   const ar_game_pod* __restrict__ games, const uint16_t* __restrict__ maze_tab, Params pr,
+                   float* __restrict__ out, int* __restrict__ error_flag) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* a_taps = smem;                                   // 9 x 16 KB im2col image
@@ -237,12 +237,18 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
       const int pidx = t * ppt + g.lp;
       const bool live = g.in_tile && pidx < n_rows;
       RowView v;
-      if (live) v = row_view(rows[pidx], games);
-      // ---- stem input: im2col of the 5-channel board (4 maze directions + cheese), k = tap * 5 + ci
+      const uint16_t* mt = nullptr;
+      if (live) {
+        const EvalRow er = rows[pidx];
+        v = row_view(er, games);
+        mt = maze_tab + (size_t)er.game_idx * MAZE_TAB_STRIDE;
+      }
+      // ---- stem input: im2col of the 5-channel board (4 maze directions from the per-game bf16
+      //      table + cheese), k = tap * 5 + ci
       {
-        float e[64];
+        uint16_t e[64];
 #pragma unroll
-        for (int k = 0; k < 64; ++k) e[k] = 0.0f;
+        for (int k = 0; k < 64; ++k) e[k] = 0;
         if (live) {
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
@@ -250,16 +256,20 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
             const int xn = g.x + dx, yn = g.y + dy;
             if (xn < 0 || xn >= W || yn < 0 || yn >= Hh) continue;
             const int nc = yn * W + xn;
-            const uint32_t mz = *reinterpret_cast<const uint32_t*>(v.maze + nc * 4);
-#pragma unroll
-            for (int d = 0; d < 4; ++d) e[tap * 5 + d] = maze_value((mz >> (8 * d)) & 0xff);
-            e[tap * 5 + 4] = ((v.cheese >> nc) & 1ull) ? 1.0f : 0.0f;
+            const uint2 m4 = __ldg(reinterpret_cast<const uint2*>(mt + nc * 4));
+            e[tap * 5 + 0] = (uint16_t)(m4.x & 0xffffu);
+            e[tap * 5 + 1] = (uint16_t)(m4.x >> 16);
+            e[tap * 5 + 2] = (uint16_t)(m4.y & 0xffffu);
+            e[tap * 5 + 3] = (uint16_t)(m4.y >> 16);
+            e[tap * 5 + 4] = ((v.cheese >> nc) & 1ull) ? BF16_ONE : (uint16_t)0;
           }
         }
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
-          uint4 pk = make_uint4(pack_bf16(e[8 * p], e[8 * p + 1]), pack_bf16(e[8 * p + 2], e[8 * p + 3]),
-                                pack_bf16(e[8 * p + 4], e[8 * p + 5]), pack_bf16(e[8 * p + 6], e[8 * p + 7]));
+          uint4 pk = make_uint4((uint32_t)e[8 * p] | ((uint32_t)e[8 * p + 1] << 16),
+                                (uint32_t)e[8 * p + 2] | ((uint32_t)e[8 * p + 3] << 16),
+                                (uint32_t)e[8 * p + 4] | ((uint32_t)e[8 * p + 5] << 16),
+                                (uint32_t)e[8 * p + 6] | ((uint32_t)e[8 * p + 7] << 16));
           *reinterpret_cast<uint4*>(a_aux + sw128_offset(r, 8 * p)) = pk;
         }
       }
@@ -614,11 +624,12 @@ struct Model : LeafEvaluator {
   }
 
   cudaError_t forward(const EvalRow* rows, const uint32_t* n_rows_dev, int n_rows_max, const ar_game_pod* games,
-                      float* out, int* error_flag, cudaStream_t stream) const override {
+                      const uint16_t* maze_tab, float* out, int* error_flag, cudaStream_t stream) const override {
     if (n_rows_max <= 0) return cudaSuccess;
     int tiles = (n_rows_max + pr.ppt - 1) / pr.ppt;
     int grid = tiles < n_sms ? tiles : n_sms;
-    cnn_forward_kernel<<<grid, THREADS, smem_bytes, stream>>>(rows, n_rows_dev, n_rows_max, games, pr, out, error_flag);
+    cnn_forward_kernel<<<grid, THREADS, smem_bytes, stream>>>(rows, n_rows_dev, n_rows_max, games, maze_tab, pr, out,
+                                                              error_flag);
     return cudaGetLastError();
   }
 };

@@ -176,6 +176,16 @@ __device__ __forceinline__ float obs_elem(const RowView& v, int k) {
 }
 
 
+constexpr uint16_t BF16_ONE = 0x3f80;
+__device__ __forceinline__ uint16_t bf16_bits(float x) {
+  __nv_bfloat16 h = __float2bfloat16_rn(x);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+// store one bf16 element (row r, column k) of a K-major SW128 operand made of [128 x 64] blocks
+__device__ __forceinline__ void put_elem(uint8_t* a_blocks, int block_bytes, int r, int k, uint16_t bits) {
+  *reinterpret_cast<uint16_t*>(a_blocks + (k >> 6) * block_bytes + sw128_offset(r, k & 63)) = bits;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

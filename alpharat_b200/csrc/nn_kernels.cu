@@ -27,6 +27,25 @@
 
 namespace ar {
 
+__global__ void maze_table_kernel(const ar_game_pod* __restrict__ games, int n, uint16_t* __restrict__ out) {
+  const int g = blockIdx.x, k = threadIdx.x;
+  if (g >= n) return;
+  const ar_game_pod& pod = games[g];
+  const int cells = (int)pod.width * pod.height;
+  float v = 0.0f;
+  if (k < cells * 4) {
+    const int c = pod.move_cost[k];
+    v = c == 0 ? -1.0f : (c >= 2 ? (float)c / 10.0f : 1.0f / 10.0f);
+  }
+  out[(size_t)g * MAZE_TAB_STRIDE + k] = k < cells * 4 ? bf16_bits(v) : (uint16_t)0;
+}
+
+cudaError_t build_maze_table(const ar_game_pod* games, int n, uint16_t* out, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  maze_table_kernel<<<n, MAZE_TAB_STRIDE, 0, stream>>>(games, n, out);
+  return cudaGetLastError();
+}
+
 __global__ void encode_f32_kernel(const EvalRow* rows, int n, const ar_game_pod* games, int obs_dim,
                                   float* out) {
   int i = blockIdx.x;
@@ -56,8 +75,8 @@ struct MlpSmem {
 // t), warp 4: TMA weight producer, warp 5: MMA issuer (and TMEM allocation).
 __global__ void __launch_bounds__(MLP_THREADS, 1)
 mlp_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict__ n_rows_ptr, int n_rows_arg,
-                   const ar_game_pod* __restrict__ games, MlpWeights w, float* __restrict__ out,
-                   int* __restrict__ error_flag) {
+                   const ar_game_pod* __restrict__ games, const uint16_t* __restrict__ maze_tab, MlpWeights w,
+                   float* __restrict__ out, int* __restrict__ error_flag) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* xa = smem;                                  // A operand / hidden activations
@@ -143,20 +162,32 @@ mlp_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int row = t * TILE_M + r;
       const bool live = row < n_rows;
-      // ---- encode observation -> bf16 A operand (k1b blocks of [128 x 64], SW128)
+      // ---- encode observation -> bf16 A operand (k1b blocks of [128 x 64], SW128): the maze
+      //      channels are copied from the per-game table, the rest of the row is zeroed and the few
+      //      non-zero elements (two positions, the cheese, six scalars) are stored one by one
       {
         RowView v;
-        if (live) v = row_view(rows[row], games);
-        for (int kb = 0; kb < k1b; ++kb) {
-#pragma unroll 2
-          for (int cc = 0; cc < 8; ++cc) {
-            float e[8];
+        const uint4* mt = nullptr;
+        int n_maze_pieces = 0;
+        if (live) {
+          const EvalRow er = rows[row];
+          v = row_view(er, games);
+          mt = reinterpret_cast<const uint4*>(maze_tab + (size_t)er.game_idx * MAZE_TAB_STRIDE);
+          n_maze_pieces = (4 * v.spatial + 7) >> 3;
+        }
+        for (int p = 0; p < k1b * 8; ++p) {
+          uint4 pk = make_uint4(0, 0, 0, 0);
+          if (p < n_maze_pieces) pk = __ldg(mt + p);
+          *reinterpret_cast<uint4*>(xa + (p >> 3) * A_BLOCK_BYTES + sw128_offset(r, (p & 7) * 8)) = pk;
+        }
+        __syncwarp();  // order the 16-byte fills before the element stores below
+        if (live) {
+          const int S = v.spatial;
+          put_elem(xa, A_BLOCK_BYTES, r, 4 * S + v.p1, BF16_ONE);
+          put_elem(xa, A_BLOCK_BYTES, r, 5 * S + v.p2, BF16_ONE);
+          for (uint64_t c = v.cheese; c; c &= c - 1) put_elem(xa, A_BLOCK_BYTES, r, 6 * S + (__ffsll((long long)c) - 1), BF16_ONE);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) e[j] = live ? obs_elem(v, kb * KB + cc * 8 + j) : 0.0f;
-            uint4 pk = make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]),
-                                  pack_bf16(e[6], e[7]));
-            *reinterpret_cast<uint4*>(xa + kb * A_BLOCK_BYTES + sw128_offset(r, cc * 8)) = pk;
-          }
+          for (int j = 0; j < 6; ++j) put_elem(xa, A_BLOCK_BYTES, r, 7 * S + j, bf16_bits(obs_elem(v, 7 * S + j)));
         }
       }
       fence_proxy_async();
@@ -172,7 +203,11 @@ mlp_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
           float v[16];
           tmem_ld16(t_lane + c0, v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + __ldg(bias + c0 + j), 0.0f);
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+            v[j] = fmaxf(v[j] + b4.x, 0.0f); v[j + 1] = fmaxf(v[j + 1] + b4.y, 0.0f);
+            v[j + 2] = fmaxf(v[j + 2] + b4.z, 0.0f); v[j + 3] = fmaxf(v[j + 3] + b4.w, 0.0f);
+          }
           int kb = c0 >> 6, col = c0 & 63;
           uint4 p0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
                                 pack_bf16(v[6], v[7]));
@@ -283,7 +318,8 @@ int MlpModel::load(const ar_tensor_desc* t, int n, int width, int height, std::s
 
 // n_rows_dev != nullptr: the row count is read on device (the self-play loop never syncs).
 cudaError_t MlpModel::forward(const EvalRow* rows, const uint32_t* n_rows_dev, int n_rows_max,
-                              const ar_game_pod* games, float* out, int* error_flag, cudaStream_t stream) const {
+                              const ar_game_pod* games, const uint16_t* maze_tab, float* out, int* error_flag,
+                              cudaStream_t stream) const {
   if (n_rows_max <= 0) return cudaSuccess;
   MlpWeights w;
   w.w1 = d_w1; w.w2 = d_w2; w.w3 = d_w3;
@@ -291,8 +327,8 @@ cudaError_t MlpModel::forward(const EvalRow* rows, const uint32_t* n_rows_dev, i
   w.k1_blocks = k1_blocks;
   int tiles = (n_rows_max + TILE_M - 1) / TILE_M;
   int grid = tiles < n_sms ? tiles : n_sms;
-  mlp_forward_kernel<<<grid, MLP_THREADS, smem_bytes, stream>>>(rows, n_rows_dev, n_rows_max, games, w, out,
-                                                                 error_flag);
+  mlp_forward_kernel<<<grid, MLP_THREADS, smem_bytes, stream>>>(rows, n_rows_dev, n_rows_max, games, maze_tab, w,
+                                                                 out, error_flag);
   return cudaGetLastError();
 }
 

@@ -82,7 +82,11 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t t_addr, const float* __
     float v[16];
     tmem_ld16(t_addr + c0, v);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j] + __ldg(bias + c0 + j), 0.0f);
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+      v[j] = fmaxf(v[j] + b4.x, 0.0f); v[j + 1] = fmaxf(v[j + 1] + b4.y, 0.0f);
+      v[j + 2] = fmaxf(v[j + 2] + b4.z, 0.0f); v[j + 3] = fmaxf(v[j + 3] + b4.w, 0.0f);
+    }
     int kb = c0 >> 6, col = c0 & 63;
     uint4 p0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     uint4 p1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
@@ -96,8 +100,8 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t t_addr, const float* __
 // warp 5: MMA issuer and TMEM owner.
 __global__ void __launch_bounds__(THREADS, 1)
 symmetric_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict__ n_rows_ptr, int n_rows_arg,
-                         const ar_game_pod* __restrict__ games, Weights w, float* __restrict__ out,
-                         int* __restrict__ error_flag) {
+                         const ar_game_pod* __restrict__ games, const uint16_t* __restrict__ maze_tab, Weights w,
+                         float* __restrict__ out, int* __restrict__ error_flag) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* r0 = smem;                           // shared_raw -> shared -> t
@@ -198,25 +202,32 @@ symmetric_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __res
       const int pidx = t * POS_PER_TILE + (r >> 1);
       const bool live = pidx < n_rows;
       {
+        // shared_raw = [maze (copied from the per-game table), cheese, progress]; player_raw =
+        // [position one-hot, mud, score]: fill with 16-byte stores, then place the few non-zeros
         RowView v;
-        if (live) v = row_view(rows[pidx], games);
-        for (int kb = 0; kb < ks; ++kb) {
-#pragma unroll 2
-          for (int cc = 0; cc < 8; ++cc) {
-            float e[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) e[j] = live ? shared_elem(v, kb * KB + cc * 8 + j) : 0.0f;
-            *reinterpret_cast<uint4*>(r0 + kb * A_BLOCK_BYTES + sw128_offset(r, cc * 8)) =
-                make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
-          }
+        const uint4* mt = nullptr;
+        int n_maze_pieces = 0;
+        if (live) {
+          const EvalRow er = rows[pidx];
+          v = row_view(er, games);
+          mt = reinterpret_cast<const uint4*>(maze_tab + (size_t)er.game_idx * MAZE_TAB_STRIDE);
+          n_maze_pieces = (4 * v.spatial + 7) >> 3;
         }
-#pragma unroll 2
-        for (int cc = 0; cc < 8; ++cc) {
-          float e[8];
+        for (int p = 0; p < ks * 8; ++p) {
+          uint4 pk = make_uint4(0, 0, 0, 0);
+          if (p < n_maze_pieces) pk = __ldg(mt + p);
+          *reinterpret_cast<uint4*>(r0 + (p >> 3) * A_BLOCK_BYTES + sw128_offset(r, (p & 7) * 8)) = pk;
+        }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) e[j] = live ? player_elem(v, cc * 8 + j, player) : 0.0f;
-          *reinterpret_cast<uint4*>(r1 + sw128_offset(r, cc * 8)) =
-              make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+        for (int p = 0; p < 8; ++p) *reinterpret_cast<uint4*>(r1 + sw128_offset(r, p * 8)) = make_uint4(0, 0, 0, 0);
+        __syncwarp();  // order the 16-byte fills before the element stores below
+        if (live) {
+          const int S = v.spatial;
+          for (uint64_t c = v.cheese; c; c &= c - 1) put_elem(r0, A_BLOCK_BYTES, r, 4 * S + (__ffsll((long long)c) - 1), BF16_ONE);
+          put_elem(r0, A_BLOCK_BYTES, r, 5 * S, bf16_bits(v.progress));
+          put_elem(r1, A_BLOCK_BYTES, r, player ? v.p2 : v.p1, BF16_ONE);
+          put_elem(r1, A_BLOCK_BYTES, r, S, bf16_bits(player_elem(v, S, player)));
+          put_elem(r1, A_BLOCK_BYTES, r, S + 1, bf16_bits(player_elem(v, S + 1, player)));
         }
       }
       fence_proxy_async();
@@ -347,12 +358,12 @@ struct Model : LeafEvaluator {
   }
 
   cudaError_t forward(const EvalRow* rows, const uint32_t* n_rows_dev, int n_rows_max, const ar_game_pod* games,
-                      float* out, int* error_flag, cudaStream_t stream) const override {
+                      const uint16_t* maze_tab, float* out, int* error_flag, cudaStream_t stream) const override {
     if (n_rows_max <= 0) return cudaSuccess;
     int tiles = (n_rows_max + POS_PER_TILE - 1) / POS_PER_TILE;
     int grid = tiles < n_sms ? tiles : n_sms;
-    symmetric_forward_kernel<<<grid, THREADS, smem_bytes, stream>>>(rows, n_rows_dev, n_rows_max, games, w, out,
-                                                                    error_flag);
+    symmetric_forward_kernel<<<grid, THREADS, smem_bytes, stream>>>(rows, n_rows_dev, n_rows_max, games, maze_tab, w,
+                                                                    out, error_flag);
     return cudaGetLastError();
   }
 };
