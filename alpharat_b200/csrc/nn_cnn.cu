@@ -64,7 +64,13 @@ struct Params {
   const float* comb_b;     // [H]
   const float* head_w;     // rows 0-4 policy_head.linear.weight, row 5 value_head.linear.weight: [6][2H]
   const float* head_b;     // [6]
+  // per-channel vectors used by every epilogue, contiguous so that they can be staged in shared
+  // memory: [b_stem 64] then per block [bn1_s 64][bn1_t 64][b1 64][pool_s 64][pool_t 64]
+  const float* vec;
+  int vec_floats;          // 64 + 320 * n_blocks
+  int vec_in_smem;         // staged (fits next to the operand buffers) or read through L1
 };
+constexpr int VEC_BLOCK = 320;
 
 struct Smem {
   uint64_t w_full[N_STAGES];
@@ -131,6 +137,7 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
   float* pool_cat = scratch + TILE_M * MAX_G;               // [MAX_PPT][2 * MAX_G]
   float* pool_out = pool_cat + MAX_PPT * 2 * MAX_G;         // [MAX_PPT][64]
   Smem* sh = reinterpret_cast<Smem*>(pool_out + MAX_PPT * C);
+  float* vec_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sh) + 128);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_rows = n_rows_ptr ? (int)*n_rows_ptr : n_rows_arg;
@@ -148,6 +155,9 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
     mbar_init(&sh->mma_done, 1);
     fence_barrier_init();
   }
+  if (pr.vec_in_smem)
+    for (int i = tid; i < pr.vec_floats; i += THREADS) vec_s[i] = __ldg(pr.vec + i);
+  const float* vec = pr.vec_in_smem ? vec_s : pr.vec;
   // out-of-board taps are never written: zero the im2col image once
   for (int i = tid; i < 10 * A_BLOCK_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 5) tmem_alloc(&sh->tmem_base, 256);
@@ -286,7 +296,7 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
             float y[16];
             tmem_ld16(TY + lane_off + c0, y);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j] + __ldg(bd.b1 + c0 + j), 0.0f);
+            for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j] + vec[64 + stage * VEC_BLOCK + 128 + c0 + j], 0.0f);
             uint4 lo, hi;
             pack16(y, lo, hi);
             if (g.in_tile) scatter_taps(a_taps, g, r, W, Hh, c0 >> 3, lo, hi);
@@ -329,13 +339,14 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
         const bool add_pool = !is_stem && pr.blocks[stage].gpool != 0;
         const bool last = stage + 1 == pr.n_blocks;
         const BlockDesc* nb = last ? nullptr : &pr.blocks[stage + 1];
+        const float* nv = vec + 64 + (stage + 1) * VEC_BLOCK;  // the next block's pre-activation vectors
 #pragma unroll 1
         for (int c0 = 0; c0 < C; c0 += 16) {
           float x[16];
           tmem_ld16(TX + lane_off + c0, x);
           if (is_stem) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j] + __ldg(pr.b_stem + c0 + j), 0.0f);
+            for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j] + vec[c0 + j], 0.0f);
           }
           if (add_pool && g.in_tile) {
 #pragma unroll
@@ -345,13 +356,13 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
           if (!last) {
             float a[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) a[j] = fmaxf(x[j] * __ldg(nb->bn1_s + c0 + j) + __ldg(nb->bn1_t + c0 + j), 0.0f);
+            for (int j = 0; j < 16; ++j) a[j] = fmaxf(x[j] * nv[c0 + j] + nv[64 + c0 + j], 0.0f);
             uint4 lo, hi;
             pack16(a, lo, hi);
             if (g.in_tile) scatter_taps(a_taps, g, r, W, Hh, c0 >> 3, lo, hi);
             if (nb->gpool) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) a[j] = fmaxf(x[j] * __ldg(nb->pool_s + c0 + j) + __ldg(nb->pool_t + c0 + j), 0.0f);
+              for (int j = 0; j < 16; ++j) a[j] = fmaxf(x[j] * nv[192 + c0 + j] + nv[256 + c0 + j], 0.0f);
               pack16(a, lo, hi);
               *reinterpret_cast<uint4*>(a_aux + sw128_offset(r, c0)) = lo;
               *reinterpret_cast<uint4*>(a_aux + sw128_offset(r, c0 + 8)) = hi;
@@ -585,6 +596,14 @@ struct Model : LeafEvaluator {
     float hb[6] = {pb[0], pb[1], pb[2], pb[3], pb[4], vb[0]};
     const size_t o_headw = fpush(hw.data(), hw.size()), o_headb = fpush(hb, 6);
 
+    std::vector<float> vecs(64 + (size_t)VEC_BLOCK * offs.size(), 0.0f);
+    memcpy(&vecs[0], &fl[o_bstem], 64 * 4);
+    for (size_t b = 0; b < offs.size(); ++b) {
+      float* d = &vecs[64 + b * VEC_BLOCK];
+      memcpy(d, &fl[offs[b].bn1_s], 256); memcpy(d + 64, &fl[offs[b].bn1_t], 256); memcpy(d + 128, &fl[offs[b].b1], 256);
+      if (offs[b].gpool) { memcpy(d + 192, &fl[offs[b].pool_s], 256); memcpy(d + 256, &fl[offs[b].pool_t], 256); }
+    }
+    const size_t o_vec = fpush(vecs.data(), vecs.size());
     const size_t fl_off = blob.size();
     blob.resize(fl_off + fl.size() * 4);
     memcpy(blob.data() + fl_off, fl.data(), fl.size() * 4);
@@ -606,6 +625,8 @@ struct Model : LeafEvaluator {
     CKN(cudaMemcpy(d_blocks, descs.data(), descs.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice));
     pr.w_stem = d_blob;
     pr.b_stem = dfl + o_bstem;
+    pr.vec = dfl + o_vec;
+    pr.vec_floats = (int)vecs.size();
     pr.blocks = d_blocks;
     pr.n_blocks = (int)descs.size();
     pr.width = width; pr.height = height; pr.ppt = ppt;
@@ -614,7 +635,9 @@ struct Model : LeafEvaluator {
     pr.comb_wT = dfl + o_combw; pr.comb_b = dfl + o_combb;
     pr.head_w = dfl + o_headw; pr.head_b = dfl + o_headb;
     smem_bytes = (size_t)10 * A_BLOCK_BYTES + N_STAGES * W_STAGE_BYTES + (size_t)TILE_M * MAX_G * 4 +
-                 (size_t)MAX_PPT * 2 * MAX_G * 4 + (size_t)MAX_PPT * C * 4 + sizeof(Smem) + 1024;
+                 (size_t)MAX_PPT * 2 * MAX_G * 4 + (size_t)MAX_PPT * C * 4 + 128 + 1024;
+    pr.vec_in_smem = smem_bytes + vecs.size() * 4 <= 227 * 1024 ? 1 : 0;
+    if (pr.vec_in_smem) smem_bytes += vecs.size() * 4;
     CKN(cudaFuncSetAttribute(cnn_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     int dev = 0;
     CKN(cudaGetDevice(&dev));
