@@ -258,10 +258,14 @@ def run_cuda(args) -> None:
         algo_bytes = BYTES_PER_NODE_VISIT * path_nodes + BYTES_PER_NEW_NODE * new_nodes
         # every rank runs its own kernel: per-GPU achieved bandwidth = per-GPU bytes / time
         achieved = algo_bytes / world / (dev_ms * 1e-3) / 1e9
+        # `traffic`: DRAM bytes of one launch.  The ncu --set full capture is taken on a bounded launch
+        # of the same kernel and workload (profiles/traffic_r1.json: measured DRAM bytes and that
+        # launch's algorithmic bytes); the ratio is applied to this run's algorithmic bytes per launch.
         traffic = None
         tp = ROOT / "profiles" / "traffic_r1.json"
         if tp.exists():
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+            tj = json.loads(tp.read_text())
+            traffic = tj["dram_bytes"] / tj["algorithmic_bytes"] * algo_bytes / max(launches, 1)
         base = cpu_baseline(args.cpu_seconds, os.cpu_count() or 1) if world == 1 and not args.no_cpu else None
         if base:
             base = {k: v for k, v in base.items() if not k.startswith("_")}
@@ -288,7 +292,9 @@ def run_cuda(args) -> None:
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": algo_bytes / max(launches, 1),
-                         "note": "tree kernel is instruction-issue bound; see profiles/"},
+                         "note": "tree kernel is instruction-issue bound (66 % of issue slots, DRAM < 2 % of peak); "
+                                 "traffic = DRAM/algorithmic ratio of the ncu capture x this run's algorithmic bytes; "
+                                 "see profiles/r1_summary.md"},
             "cpu_baseline": base,
             "clocks": clocks,
         }
