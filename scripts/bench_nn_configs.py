@@ -4,7 +4,9 @@
 
 config 3: 7x7_rust_tuned (1897 sims, c_puct 0.512, fpu 0.459, force_k 0.103), MLP, 16384 concurrent games
 config 4: 7x7_rust_strong (2693 sims, c_puct 0.512, fpu 0.479, force_k 0.025), SymmetricMLP and CNN-gpool
-Prints one JSON line per run (device time from CUDA events around the whole run)."""
+Prints one JSON line per run (device time from CUDA events around the whole run).
+Config 4 runs with 4096 resident trees: 2693-sim searches guided by a peaked value head keep most of the
+tree across moves (tens of thousands of nodes per tree), and 16384 trees would leave only 29k nodes each."""
 import json
 import sys
 
@@ -17,8 +19,8 @@ from nn_ref import make_cnn_state_dict, make_mlp_state_dict, make_symmetric_stat
 FLOPS = {"mlp": 315_904, "symmetric": 976_896, "cnn": 22.2e6}
 RUNS = {
     "mlp": dict(arch=N.AR_ARCH_MLP, sd=lambda: make_mlp_state_dict(0, 349), conc=16384, n=32768, sims=1897, fpu=0.459, fk=0.103),
-    "symmetric": dict(arch=N.AR_ARCH_SYMMETRIC, sd=lambda: make_symmetric_state_dict(2, 7, 7), conc=16384, n=32768, sims=2693, fpu=0.479, fk=0.025),
-    "cnn": dict(arch=N.AR_ARCH_CNN, sd=lambda: make_cnn_state_dict(3, ("res", "res", "gpool")), conc=16384, n=16384, sims=2693, fpu=0.479, fk=0.025),
+    "symmetric": dict(arch=N.AR_ARCH_SYMMETRIC, sd=lambda: make_symmetric_state_dict(2, 7, 7), conc=4096, n=8192, sims=2693, fpu=0.479, fk=0.025),
+    "cnn": dict(arch=N.AR_ARCH_CNN, sd=lambda: make_cnn_state_dict(3, ("res", "res", "gpool")), conc=4096, n=4096, sims=2693, fpu=0.479, fk=0.025),
 }
 for name in (sys.argv[1:] or ["mlp", "symmetric", "cnn"]):
     r = RUNS[name]
