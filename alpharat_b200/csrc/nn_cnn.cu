@@ -93,10 +93,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float v[16]) {
 }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-__device__ __forceinline__ float maze_value(int c) {  // flat_encoder.rs:62-80
-  return c == 0 ? -1.0f : (c >= 2 ? (float)c / 10.0f : 1.0f / 10.0f);
-}
-
 // Geometry of the tile row owned by an epilogue thread.
 struct RowGeo {
   int lp, cell, x, y;

@@ -53,17 +53,7 @@ struct Smem {
   uint32_t tmem_base;
 };
 
-// [maze(4S), cheese(S), progress] — symmetric.py:137-147
-__device__ __forceinline__ float shared_elem(const RowView& v, int k) {
-  const int S = v.spatial;
-  if (k < 4 * S) {
-    int c = v.maze[k];
-    return c == 0 ? -1.0f : (c >= 2 ? (float)c / 10.0f : 1.0f / 10.0f);
-  }
-  k -= 4 * S;
-  if (k < S) return ((v.cheese >> k) & 1ull) ? 1.0f : 0.0f;
-  return k == S ? v.progress : 0.0f;
-}
+// shared_raw = [maze(4S), cheese(S), progress] — symmetric.py:137-147 (assembled in the kernel)
 // [pos one-hot(S), mud, score] — symmetric.py:150-165
 __device__ __forceinline__ float player_elem(const RowView& v, int k, int player) {
   const int S = v.spatial;

@@ -1,0 +1,114 @@
+"""Edge cases of the uniform-prior path on the GPU, bit-exact against the oracle: empty and ragged inputs,
+the largest board (64 cells), the largest batch, aggressive collision budgets (the multi-visit level
+builder), games that are over before they start, and the loud failures."""
+
+from __future__ import annotations
+
+import pytest
+
+from alpharat_b200.engine import Engine, search_cfg
+from alpharat_b200.games import GameSpec, make_games, pods_array
+from conftest import oracle_search, oracle_selfplay
+from test_gpu_parity_uniform import assert_result_equal, compare_selfplay
+
+pytestmark = pytest.mark.gpu
+
+
+def test_empty_inputs():
+    cfg = search_cfg(simulations=50, batch_size=8)
+    with Engine(concurrent_games=8, max_turns=30, max_batch_size=8, max_simulations=50) as eng:
+        summ, pos, stride, st = eng.selfplay(pods_array([]), cfg, [])
+        assert st.total_games == 0 and st.total_positions == 0 and st.total_simulations == 0
+        assert len(eng.search_batch(pods_array([]), cfg, [])) <= 1
+
+
+def test_ragged_boards_and_lengths_in_one_call(oracle):
+    """Boards of different sizes and max_turns share one call and fewer slots than games."""
+    specs = (make_games(6, width=5, height=5, cheese_count=5, max_turns=12)
+             + make_games(5, width=7, height=7, cheese_count=10, max_turns=25, first_index=40)
+             + make_games(4, width=7, height=5, cheese_count=6, max_turns=9, maze_type="classic", positions="random")
+             + make_games(3, width=8, height=8, cheese_count=12, max_turns=17, first_index=70)
+             + [GameSpec(4, 3, 5, (0, 0), (3, 2), [(1, 1), (2, 1)])])
+    pods = pods_array(specs)
+    n = len(specs)
+    cfg = search_cfg(simulations=120, batch_size=8)
+    seeds = [3 * i + 1 for i in range(n)]
+    with Engine(concurrent_games=5, max_turns=25, max_batch_size=8, max_simulations=120) as eng:
+        gpu = eng.selfplay(pods, cfg, seeds)
+    cpu = oracle_selfplay(oracle, pods, cfg, seeds)
+    compare_selfplay(gpu, cpu, n)
+
+
+def test_full_bitboard_8x8_and_max_batch(oracle):
+    specs = make_games(10, width=8, height=8, cheese_count=20, max_turns=20, first_index=11)
+    pods = pods_array(specs)
+    cfg = search_cfg(simulations=400, batch_size=64, c_puct=1.1, fpu_reduction=0.3, force_k=1.0,
+                     collision_limit_min=4, collision_limit_max=64, collision_scaling_start=20,
+                     collision_scaling_end=600, collision_scaling_power=0.7)
+    seeds = [100 + i for i in range(10)]
+    with Engine(concurrent_games=10, max_turns=20, max_batch_size=64, max_simulations=400) as eng:
+        gpu = eng.selfplay(pods, cfg, seeds)
+    cpu = oracle_selfplay(oracle, pods, cfg, seeds)
+    compare_selfplay(gpu, cpu, 10)
+    assert gpu[3].total_collisions > 0
+
+
+def test_multi_visit_levels_and_tiny_searches(oracle):
+    """Collision budgets far above 1 from the first batch (general build_gather_level with visits-to-change
+    estimates and parked levels), and searches smaller than one batch."""
+    specs = make_games(12, width=7, height=7, cheese_count=10, max_turns=50, first_index=300)
+    pods = pods_array(specs)
+    for sims, bs in ((3, 16), (16, 16), (500, 16), (257, 5)):
+        cfg = search_cfg(simulations=sims, batch_size=bs, c_puct=0.512, fpu_reduction=0.459, force_k=0.103,
+                         collision_limit_min=8, collision_limit_max=200, collision_scaling_start=0,
+                         collision_scaling_end=300, collision_scaling_power=1.0)
+        seeds = [sims + 13 * i for i in range(12)]
+        with Engine(concurrent_games=12, max_turns=50, max_batch_size=16, max_simulations=sims, pool_nodes=2048) as eng:
+            out = eng.search_batch(pods, cfg, seeds)
+        for i in range(12):
+            rc, ref, clean = oracle_search(oracle, pods[i], cfg, seeds[i])
+            assert rc == 0 and clean
+            assert_result_equal(out[i], ref, f"sims={sims} bs={bs} pos {i}")
+
+
+def test_games_that_are_over_before_they_start(oracle):
+    specs = [GameSpec(5, 5, 10, (0, 0), (4, 4), [(2, 2)], turn=10),          # turn == max_turns
+             GameSpec(5, 5, 10, (0, 0), (4, 4), [], turn=0),                  # no cheese
+             GameSpec(5, 5, 10, (0, 0), (4, 4), [(2, 2)], p1_score=3.0),      # P1 already has the majority
+             GameSpec(5, 5, 10, (1, 1), (3, 3), [(2, 2), (0, 4)])]            # a normal game next to them
+    pods = pods_array(specs)
+    cfg = search_cfg(simulations=60, batch_size=8)
+    with Engine(concurrent_games=2, max_turns=10, max_batch_size=8, max_simulations=60) as eng:
+        gpu = eng.selfplay(pods, cfg, [5, 6, 7, 8])
+    cpu = oracle_selfplay(oracle, pods, cfg, [5, 6, 7, 8])
+    compare_selfplay(gpu, cpu, 4)
+    assert [gpu[0][i].n_positions for i in range(3)] == [0, 0, 0] and gpu[0][3].n_positions > 0
+
+
+def test_results_do_not_depend_on_the_number_of_resident_trees():
+    specs = make_games(24, width=5, height=5, cheese_count=5, max_turns=15)
+    pods = pods_array(specs)
+    cfg = search_cfg(simulations=80, batch_size=8)
+    seeds = list(range(24))
+    runs = []
+    for conc in (1, 7, 24):
+        with Engine(concurrent_games=conc, max_turns=15, max_batch_size=8, max_simulations=80) as eng:
+            runs.append(eng.selfplay(pods, cfg, seeds))
+    compare_selfplay(runs[0], runs[1], 24)
+    compare_selfplay(runs[0], runs[2], 24)
+
+
+def test_loud_failures():
+    specs = make_games(4, width=7, height=7, cheese_count=10, max_turns=50)
+    pods = pods_array(specs)
+    with Engine(concurrent_games=4, max_turns=50, max_batch_size=8, max_simulations=2000, pool_nodes=256) as eng:
+        with pytest.raises(ValueError, match="batch_size"):
+            eng.selfplay(pods, search_cfg(simulations=100, batch_size=16), [0, 1, 2, 3])
+        with pytest.raises(RuntimeError, match="pool"):  # 2000 simulations cannot fit 256 nodes
+            eng.selfplay(pods, search_cfg(simulations=2000, batch_size=8), [0, 1, 2, 3])
+        with pytest.raises(ValueError, match="max_turns"):
+            eng.selfplay(pods_array(make_games(1, width=5, height=5, cheese_count=5, max_turns=80)),
+                         search_cfg(simulations=10, batch_size=8), [0])
+        with pytest.raises((NotImplementedError, RuntimeError), match="64-cell"):  # 81 cells > the 64-cell bitboard
+            eng.selfplay(pods_array([GameSpec(9, 9, 10, (0, 0), (8, 8), [(4, 4)])]),
+                         search_cfg(simulations=10, batch_size=8), [0])
