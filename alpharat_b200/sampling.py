@@ -1,0 +1,244 @@
+"""`run_cuda_sampling` — drop-in for `run_rust_sampling` (alpharat/data/rust_sampling.py:137-296).
+
+Same keyword arguments, same `(batch_dir, metrics)` return value, same ExperimentManager protocol
+(`prepare_batch` before play, `register_batch` only after success, bundles under `batch_dir/games`).
+Differences that come with `backend: cuda`:
+
+* the `.pt` checkpoint is handed to the engine as it is (no ONNX export, rust_sampling.py:118-134);
+* `device` names a GPU (`"cuda"`, `"cuda:3"`, `"b200"`, an int) instead of an ONNX execution provider;
+* `num_threads` / `mux_max_batch_size` are accepted and ignored (no host worker pool, no mux);
+* `mcts` is a `CudaMCTSConfig` (its `concurrent_games`, `pool_nodes`, `seed` are passed through); a
+  `RustMCTSConfig` works too — only the shared search fields are read.
+
+The reference package owns `ExperimentManager`; it is imported from `alpharat.experiments` when the caller
+does not pass one (any object with `prepare_batch` / `register_batch` of the same signature will do, which
+is also how the tests drive this function without the reference installed).
+"""
+
+from __future__ import annotations
+
+import logging
+import threading
+import time
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Any
+
+from .selfplay import SelfPlayProgress, cuda_self_play
+
+logger = logging.getLogger(__name__)
+
+_SEARCH_FIELDS = (
+    "simulations", "batch_size", "c_puct", "fpu_reduction", "force_k", "noise_epsilon", "noise_concentration",
+    "collision_limit_min", "collision_limit_max", "collision_scaling_start", "collision_scaling_end",
+    "collision_scaling_power",
+)
+
+
+def resolve_sampling_device(device: str | int) -> int:
+    """GPU ordinal for a user-facing device name (rust_sampling.py:23-32 maps to ORT providers instead)."""
+    if isinstance(device, int):
+        return device
+    d = device.lower()
+    if d in ("auto", "cuda", "b200", "gpu", "tensorrt"):
+        return 0
+    for prefix in ("cuda:", "b200:", "gpu:"):
+        if d.startswith(prefix) and d[len(prefix):].isdigit():
+            return int(d[len(prefix):])
+    raise ValueError(f"backend cuda cannot run on device {device!r} (expected 'cuda', 'cuda:<n>' or an int)")
+
+
+def resolve_training_device(device: str | int) -> str:
+    """PyTorch device for the training half of an iterate loop (rust_sampling.py:35-45)."""
+    return f"cuda:{resolve_sampling_device(device)}"
+
+
+@dataclass
+class CudaSamplingMetrics:
+    """Field-for-field twin of `RustSamplingMetrics` (rust_sampling.py:48-115)."""
+
+    total_games: int
+    total_positions: int
+    total_simulations: int
+    elapsed_seconds: float
+    p1_wins: int
+    p2_wins: int
+    draws: int
+    total_cheese_collected: float
+    total_cheese_available: int
+    min_turns: int
+    max_turns: int
+    total_nn_evals: int
+    total_terminals: int
+    total_collisions: int
+    cache_hits: int
+    cache_misses: int
+
+    def _rate(self, x: float) -> float:
+        return x / self.elapsed_seconds if self.elapsed_seconds > 0 else 0.0
+
+    games_per_second = property(lambda s: s._rate(s.total_games))
+    positions_per_second = property(lambda s: s._rate(s.total_positions))
+    simulations_per_second = property(lambda s: s._rate(s.total_simulations))
+    nn_evals_per_second = property(lambda s: s._rate(s.total_nn_evals))
+
+    @property
+    def avg_turns(self) -> float:
+        return self.total_positions / self.total_games if self.total_games > 0 else 0.0
+
+    @property
+    def cheese_utilization(self) -> float:
+        return self.total_cheese_collected / self.total_cheese_available if self.total_cheese_available else 0.0
+
+    @property
+    def draw_rate(self) -> float:
+        return self.draws / self.total_games if self.total_games > 0 else 0.0
+
+    @property
+    def nn_eval_fraction(self) -> float:
+        return self.total_nn_evals / self.total_simulations if self.total_simulations > 0 else 0.0
+
+    @property
+    def terminal_fraction(self) -> float:
+        return self.total_terminals / self.total_simulations if self.total_simulations > 0 else 0.0
+
+    @property
+    def collision_fraction(self) -> float:
+        total = self.total_nn_evals + self.total_terminals + self.total_collisions
+        return self.total_collisions / total if total > 0 else 0.0
+
+    @property
+    def cache_hit_rate(self) -> float:
+        total = self.cache_hits + self.cache_misses
+        return self.cache_hits / total if total > 0 else 0.0
+
+
+def self_play_kwargs(game: Any, mcts: Any, num_games: int) -> dict[str, Any]:
+    """Nested `GameConfig` + MCTS config -> flat `cuda_self_play` keywords (rust_sampling.py:198-238).
+
+    `game` is read duck-typed: `width, height, max_turns, positions, cheese.{count,symmetric}, maze.type`
+    and, for random mazes, `maze.{wall_density,mud_density,symmetric}` (alpharat/config/game.py:46-52).
+    """
+    kwargs: dict[str, Any] = {
+        "width": game.width,
+        "height": game.height,
+        "cheese_count": game.cheese.count,
+        "max_turns": game.max_turns,
+        "num_games": num_games,
+        "maze_type": game.maze.type,
+        "cheese_symmetric": game.cheese.symmetric,
+        "positions": game.positions,
+    }
+    if getattr(game.maze, "type", None) == "random":
+        kwargs["wall_density"] = game.maze.wall_density
+        kwargs["mud_density"] = game.maze.mud_density
+        kwargs["maze_symmetric"] = game.maze.symmetric
+    for f in _SEARCH_FIELDS:
+        kwargs[f] = getattr(mcts, f)
+    for f in ("concurrent_games", "pool_nodes", "seed"):  # CudaMCTSConfig only
+        if hasattr(mcts, f):
+            kwargs[f] = getattr(mcts, f)
+    return kwargs
+
+
+def run_cuda_sampling(
+    *,
+    game: Any,
+    mcts: Any,
+    num_games: int,
+    group: str,
+    num_threads: int = 4,
+    max_games_per_bundle: int = 32,
+    mux_max_batch_size: int = 256,
+    checkpoint: str | None = None,
+    device: str | int = "cuda",
+    cache_size: int = 0,
+    experiments_dir: str | Path = "experiments",
+    verbose: bool = True,
+    experiment_manager: Any | None = None,
+    self_play_fn: Any = cuda_self_play,
+) -> tuple[Path, CudaSamplingMetrics]:
+    """Create a batch, play `num_games` games on the GPU into it, register it; returns `(batch_dir, metrics)`.
+
+    Raises whatever `cuda_self_play` raises (`RuntimeError` engine, `IOError` bundle writing); the batch is
+    registered only when play succeeded, exactly like the reference (rust_sampling.py:246-254).
+    """
+    exp = experiment_manager
+    if exp is None:
+        from alpharat.experiments import ExperimentManager  # type: ignore[import-not-found]
+
+        exp = ExperimentManager(Path(experiments_dir))
+    if getattr(mcts, "device_ids", None) and device in ("cuda", "auto"):
+        device = mcts.device_ids[0]
+
+    batch_dir, batch_uuid = exp.prepare_batch(group=group, mcts_config=mcts, game=game, checkpoint_path=checkpoint)
+    output_dir = Path(batch_dir) / "games"
+
+    kwargs = self_play_kwargs(game, mcts, num_games)
+    kwargs.update(
+        num_threads=num_threads,
+        output_dir=str(output_dir),
+        max_games_per_bundle=max_games_per_bundle,
+        mux_max_batch_size=mux_max_batch_size,
+        checkpoint=checkpoint,
+        device=resolve_sampling_device(device),
+        cache_size=cache_size,
+    )
+    stats = _run_with_progress(self_play_fn, kwargs, num_games) if verbose else self_play_fn(**kwargs)
+
+    exp.register_batch(group=group, batch_uuid=batch_uuid, mcts_config=mcts, game=game, checkpoint_path=checkpoint)
+
+    metrics = CudaSamplingMetrics(
+        total_games=stats.total_games,
+        total_positions=stats.total_positions,
+        total_simulations=stats.total_simulations,
+        elapsed_seconds=stats.elapsed_secs,
+        p1_wins=stats.p1_wins,
+        p2_wins=stats.p2_wins,
+        draws=stats.draws,
+        total_cheese_collected=stats.total_cheese_collected,
+        total_cheese_available=stats.total_cheese_available,
+        min_turns=stats.min_turns,
+        max_turns=stats.max_turns,
+        total_nn_evals=stats.total_nn_evals,
+        total_terminals=stats.total_terminals,
+        total_collisions=stats.total_collisions,
+        cache_hits=stats.cache_hits,
+        cache_misses=stats.cache_misses,
+    )
+    logger.info(
+        "CUDA self-play complete: %d games, %d positions, %.0f sims/s (%.0f nn_evals/s, %.0f%% nn, %.1fs)",
+        metrics.total_games, metrics.total_positions, metrics.simulations_per_second,
+        metrics.nn_evals_per_second, metrics.nn_eval_fraction * 100, metrics.elapsed_seconds,
+    )
+    return Path(batch_dir), metrics
+
+
+def _run_with_progress(self_play_fn: Any, kwargs: dict[str, Any], num_games: int) -> Any:
+    """Play in a background thread and poll the live counters (rust_sampling.py:299-338)."""
+    from tqdm import tqdm
+
+    progress = SelfPlayProgress()
+    kwargs["progress"] = progress
+    result: list[Any] = []
+    error: list[BaseException] = []
+
+    def _worker() -> None:
+        try:
+            result.append(self_play_fn(**kwargs))
+        except BaseException as e:  # re-raised on the caller's thread
+            error.append(e)
+
+    thread = threading.Thread(target=_worker, daemon=True)
+    thread.start()
+    with tqdm(total=num_games, desc="CUDA self-play", unit="game") as pbar:
+        while thread.is_alive():
+            pbar.n = progress.games_completed
+            pbar.refresh()
+            time.sleep(0.2)
+        pbar.n = progress.games_completed
+        pbar.refresh()
+    thread.join()
+    if error:
+        raise error[0]
+    return result[0]

@@ -112,3 +112,41 @@ def test_loud_failures():
         with pytest.raises((NotImplementedError, RuntimeError), match="64-cell"):  # 81 cells > the 64-cell bitboard
             eng.selfplay(pods_array([GameSpec(9, 9, 10, (0, 0), (8, 8), [(4, 4)])]),
                          search_cfg(simulations=10, batch_size=8), [0])
+
+
+def test_run_cuda_sampling_writes_a_registered_batch(oracle, tmp_path):
+    """The `run_rust_sampling` drop-in end to end on the GPU: the bundles it leaves in the batch directory hold
+    the oracle's games for the same seed (visit tables and actions bit for bit)."""
+    import numpy as np
+
+    from alpharat_b200 import CudaMCTSConfig
+    from alpharat_b200.sampling import run_cuda_sampling
+    from test_host_api import _FakeManager, _Game
+
+    mgr = _FakeManager(tmp_path)
+    mcts = CudaMCTSConfig(simulations=60, batch_size=8, concurrent_games=16, seed=5)
+    batch_dir, m = run_cuda_sampling(game=_Game(), mcts=mcts, num_games=9, group="uniform_5x5",
+                                     max_games_per_bundle=4, verbose=True, experiment_manager=mgr)
+    assert len(mgr.registered) == 1 and m.total_games == 9
+    files = sorted((batch_dir / "games").glob("bundle_*.npz"))
+    assert len(files) == 3
+    specs = make_games(9, width=5, height=5, cheese_count=5, max_turns=30)
+    cfg = search_cfg(simulations=60, batch_size=8)
+    summ, pos, stride, st = oracle_selfplay(oracle, pods_array(specs), cfg, [5 + i for i in range(9)])
+    assert (m.total_positions, m.total_simulations, m.p1_wins, m.p2_wins, m.draws) == (
+        st.total_positions, st.total_simulations, st.p1_wins, st.p2_wins, st.draws)
+    want = {}
+    for g in range(9):
+        k = summ[g].n_positions
+        acts = tuple((pos[g * stride + t].action_p1, pos[g * stride + t].action_p2) for t in range(k))
+        vis = tuple(tuple(float(v) for v in pos[g * stride + t].search.visit_counts_p1) for t in range(k))
+        want[(acts, vis)] = want.get((acts, vis), 0) + 1
+    got = {}
+    for f in files:
+        z = np.load(f)
+        ends = np.cumsum(z["game_lengths"])
+        for b, e in zip(np.concatenate([[0], ends[:-1]]), ends):
+            acts = tuple(zip(z["action_p1"][b:e].tolist(), z["action_p2"][b:e].tolist()))
+            vis = tuple(tuple(float(v) for v in row) for row in z["visit_counts_p1"][b:e])
+            got[(acts, vis)] = got.get((acts, vis), 0) + 1
+    assert got == want

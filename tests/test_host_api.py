@@ -173,3 +173,112 @@ def test_bundle_format(oracle, tmp_path):
         assert (z["cheese_mask"][first] == z["initial_cheese"]).all() and (z["turn"][first] == 0).all()
         assert set(np.unique(z["cheese_outcomes"])) <= {0, 1, 2, 3}
     assert total_games == n and total_pos == st.total_positions
+
+
+# ---- run_cuda_sampling (drop-in for run_rust_sampling, alpharat/data/rust_sampling.py:137-296) -----------
+class _Cheese:
+    count, symmetric = 5, True
+
+
+class _OpenMaze:
+    type = "open"
+
+
+class _RandomMaze:
+    type, wall_density, mud_density, symmetric = "random", 0.5, 0.2, False
+
+
+class _Game:
+    width, height, max_turns, positions = 5, 5, 30, "corners"
+    cheese = _Cheese()
+
+    def __init__(self, maze=None):
+        self.maze = maze or _OpenMaze()
+
+    def model_dump(self):
+        return {"width": 5, "height": 5}
+
+
+class _FakeManager:
+    """prepare_batch / register_batch with the signatures of experiments/manager.py:161-245."""
+
+    def __init__(self, root):
+        self.root, self.registered, self.prepared = Path(root), [], []
+
+    def prepare_batch(self, group, mcts_config, game, checkpoint_path=None):
+        d = self.root / "batches" / group / f"uuid{len(self.prepared)}"
+        (d / "games").mkdir(parents=True)
+        self.prepared.append((group, d.name, mcts_config, checkpoint_path))
+        return d, d.name
+
+    def register_batch(self, group, batch_uuid, mcts_config, game, checkpoint_path=None, created_at=None):
+        self.registered.append((group, batch_uuid, mcts_config.model_dump(), checkpoint_path))
+
+
+def test_run_cuda_sampling_signature_covers_run_rust_sampling():
+    from alpharat_b200.sampling import CudaSamplingMetrics, run_cuda_sampling
+
+    ref = ("game mcts num_games group num_threads max_games_per_bundle mux_max_batch_size checkpoint device "
+           "cache_size experiments_dir verbose").split()
+    params = inspect.signature(run_cuda_sampling).parameters
+    assert [p for p in ref if p not in params] == []
+    ref_metrics = ("total_games total_positions total_simulations elapsed_seconds p1_wins p2_wins draws "
+                   "total_cheese_collected total_cheese_available min_turns max_turns total_nn_evals "
+                   "total_terminals total_collisions cache_hits cache_misses").split()
+    assert list(CudaSamplingMetrics.__dataclass_fields__) == ref_metrics
+    for derived in ("games_per_second positions_per_second simulations_per_second avg_turns cheese_utilization "
+                    "draw_rate nn_evals_per_second nn_eval_fraction terminal_fraction collision_fraction "
+                    "cache_hit_rate").split():
+        assert isinstance(getattr(CudaSamplingMetrics, derived), property)
+
+
+def test_run_cuda_sampling_batch_protocol(oracle, tmp_path):
+    """prepare -> play into batch_dir/games -> register only on success; kwargs flattened like the reference."""
+    from alpharat_b200.sampling import resolve_sampling_device, run_cuda_sampling, self_play_kwargs
+    from alpharat_b200.selfplay import SelfPlayStats
+
+    seen = {}
+
+    def oracle_backed_self_play(**kw):  # stands in for the GPU engine on a CPU-only box
+        seen.update(kw)
+        specs = make_games(kw["num_games"], width=kw["width"], height=kw["height"], cheese_count=kw["cheese_count"],
+                           max_turns=kw["max_turns"])
+        cfg = search_cfg(simulations=kw["simulations"], batch_size=kw["batch_size"], c_puct=kw["c_puct"])
+        summ, pos, stride, st = oracle_selfplay(oracle, pods_array(specs), cfg, list(range(len(specs))), n_threads=2)
+        write_bundles(Path(kw["output_dir"]), specs, summ, pos, stride, kw["max_games_per_bundle"])
+        st.elapsed_secs = 0.5
+        if kw.get("progress") is not None:
+            assert kw["progress"].games_completed == 0
+        return SelfPlayStats(st)
+
+    mgr = _FakeManager(tmp_path)
+    mcts = ab.CudaMCTSConfig(simulations=40, batch_size=8, c_puct=1.5, concurrent_games=64, seed=11)
+    batch_dir, m = run_cuda_sampling(game=_Game(), mcts=mcts, num_games=6, group="uniform_5x5",
+                                     max_games_per_bundle=4, device="cuda:0", verbose=False,
+                                     experiment_manager=mgr, self_play_fn=oracle_backed_self_play)
+    assert batch_dir == tmp_path / "batches" / "uniform_5x5" / "uuid0"
+    assert mgr.registered == [("uniform_5x5", "uuid0", mcts.model_dump(), None)]
+    assert mgr.registered[0][2]["backend"] == "cuda"
+    assert len(list((batch_dir / "games").glob("bundle_*.npz"))) == 2
+    assert seen["output_dir"] == str(batch_dir / "games") and seen["device"] == 0
+    assert (seen["concurrent_games"], seen["seed"], seen["simulations"], seen["maze_type"]) == (64, 11, 40, "open")
+    assert "wall_density" not in seen and seen["cheese_symmetric"] is True and seen["positions"] == "corners"
+    assert m.total_games == 6 and m.total_positions > 0 and m.elapsed_seconds == 0.5
+    assert m.games_per_second == 12.0 and 0 < m.cheese_utilization <= 1 and m.avg_turns == m.total_positions / 6
+    assert m.p1_wins + m.p2_wins + m.draws == 6
+
+    kw = self_play_kwargs(_Game(_RandomMaze()), ab.RustMCTSConfig(simulations=7), 3)
+    assert (kw["wall_density"], kw["mud_density"], kw["maze_symmetric"], kw["simulations"]) == (0.5, 0.2, False, 7)
+    assert "concurrent_games" not in kw  # a RustMCTSConfig carries only the shared search fields
+
+    def failing(**kw):
+        raise RuntimeError("engine failure")
+
+    with pytest.raises(RuntimeError, match="engine failure"):
+        run_cuda_sampling(game=_Game(), mcts=mcts, num_games=2, group="g", verbose=True,
+                          experiment_manager=mgr, self_play_fn=failing)
+    assert len(mgr.prepared) == 2 and len(mgr.registered) == 1  # failed batch prepared, never registered
+
+    assert [resolve_sampling_device(d) for d in ("auto", "cuda", "cuda:3", "b200", 5)] == [0, 0, 3, 0, 5]
+    with pytest.raises(ValueError):
+        resolve_sampling_device("coreml")
