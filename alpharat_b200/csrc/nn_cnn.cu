@@ -11,16 +11,22 @@
 // Supported: C = 64 trunk channels, any sequence of res / gpool blocks (gpool_channels 16 or 32),
 // P <= 32, H <= 64, `mlp` policy head and `point` value head (configs/model/cnn*.yaml).
 //
-// B200 mapping: a 3x3 convolution over a tile of `ppt` positions (ppt * S <= 128 spatial rows, one
-// row per TMEM lane) is an implicit GEMM with M = 128, N = 64, K = 9 taps x 64 channels.  The A
-// operand is an im2col image in shared memory: 9 K-blocks of [128 x 64] bf16, 128B-swizzled, where
-// block `tap` row r' holds the activations of r' + tap offset (zero outside the board).  The
-// epilogue thread that owns a row scatters its 128-byte activation vector into the 9 tap blocks.
+// B200 mapping: a 3x3 convolution is an implicit GEMM with M = 128 spatial rows (one row per TMEM
+// lane), N = 64, K = 9 taps x 64 channels, and the im2col image is never materialised.  A position's
+// board is laid out with one zero column and one zero row of padding ((w+1) x (h+1) rows), so the
+// input of tap (dy, dx) for tile row r is simply row r + dy * (w+1) + dx of the same activation buffer:
+// every tap is the same 128B-swizzled K-major operand read through a shared-memory descriptor whose
+// start address is shifted by whole rows (the swizzle is a function of the shared-memory address, and
+// the buffer is written with the same address-based swizzle).  An epilogue thread therefore stores
+// its 128-byte activation vector once instead of nine times, and out-of-board taps read the padding.
+// A CTA owns NG = 2 such 128-row groups (two TMEM accumulator sets) that share every weight stage, so
+// each 8 KB weight tap streamed by the TMA bulk-copy ring feeds 2 x 4 MMAs and 8 epilogue warps.
 // The residual stream never leaves TMEM: conv2 accumulates straight onto it (accumulate = 1 from
 // the first MMA), conv1 goes to a second accumulator, the gpool 1x1 convolution to a third.
-// Weights stream tap by tap (8 KB) through a 4-stage TMA bulk-copy ring.  BatchNorms that follow
-// a convolution are folded into its weights; pre-activation BatchNorms are applied in the epilogue.
-// The tiny per-player head (3 -> P -> H -> 6) runs on CUDA cores from shared memory.
+// BatchNorms that follow a convolution are folded into its weights; pre-activation BatchNorms are
+// applied in the epilogue.  The tiny per-player head (3 -> P -> H -> 6) runs on CUDA cores.
+#include <cstdlib>
+
 #include "nn_common.cuh"
 
 namespace ar {
@@ -28,14 +34,24 @@ namespace cnn {
 
 constexpr int TILE_M = 128;
 constexpr int C = 64;
-constexpr int A_BLOCK_BYTES = TILE_M * KB * 2;   // 16 KB: one tap of the im2col image
+#ifndef AR_CNN_NG
+#define AR_CNN_NG 1
+#endif
+constexpr int NG = AR_CNN_NG;                    // 128-row groups per CTA (1: two CTAs share an SM)
+constexpr int CTAS_PER_SM = NG == 1 ? 2 : 1;
+constexpr int EPI_THREADS = TILE_M * NG;
+constexpr int THREADS = EPI_THREADS + 64;        // + TMA warp + MMA warp
+constexpr int GUARD = 16;                        // zero rows before / after a group's activation rows
+constexpr int A_BYTES = (TILE_M + 2 * GUARD) * 128;  // 20 KB activation buffer of one group
+constexpr int AUX_BYTES = TILE_M * KB * 2;       // 16 KB: stem input / gpool 1x1 input of one group
 constexpr int W_STAGE_BYTES = C * KB * 2;        // 8 KB: one tap of one convolution
-constexpr int N_STAGES = 4;
-constexpr int THREADS = 192;
+constexpr int N_STAGES = NG == 1 ? 8 : 14;      // a 3x3 convolution is 9 stages
 constexpr int MAX_BLOCKS = 16;
-constexpr int MAX_PPT = 8;                       // positions per tile (boards smaller than 4x4 waste rows)
+constexpr int MAX_PPT = 8;                       // positions per group
 constexpr int MAX_G = 32;                        // gpool channels
 constexpr int MAX_P = 32, MAX_H = 64;
+constexpr int CAT = C + MAX_P;                    // row stride of the combiner input [f_i | e_i]
+constexpr int TMEM_COLS_PER_GROUP = 256;         // X 64 | Y 64 | P 32
 
 struct BlockDesc {
   int gpool;               // 0 res, >0: gpool channels
@@ -56,7 +72,7 @@ struct Params {
   const float* b_stem;     // [64]
   const BlockDesc* blocks;
   int n_blocks;
-  int width, height, ppt;
+  int width, height, ppt;  // ppt = positions per 128-row group
   int P, H;
   const float* enc_w;      // player_encoder.0.weight [P][3]
   const float* enc_b;      // [P]
@@ -69,6 +85,7 @@ struct Params {
   const float* vec;
   int vec_floats;          // 64 + 320 * n_blocks
   int vec_in_smem;         // staged (fits next to the operand buffers) or read through L1
+  int desc_mode;           // descriptor base-offset convention for row-shifted operands (0 = none)
 };
 constexpr int VEC_BLOCK = 320;
 
@@ -91,80 +108,141 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float v[16]) {
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-// Geometry of the tile row owned by an epilogue thread.
-struct RowGeo {
-  int lp, cell, x, y;
-  bool in_tile;  // row belongs to one of the tile's ppt positions
-};
-
-// Scatter 16 channels (pieces p0, p0+1 of the 128-byte activation vector of row r) into the 9 tap
-// blocks of the im2col image: block `tap` row r' = r - (dy * w + dx) holds in[r' + (dy, dx)].
-__device__ __forceinline__ void scatter_taps(uint8_t* a_taps, const RowGeo& g, int r, int w, int h, int p0,
-                                             uint4 lo, uint4 hi) {
-#pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-    const int xo = g.x - dx, yo = g.y - dy;  // the output cell that reads this row through `tap`
-    if (xo < 0 || xo >= w || yo < 0 || yo >= h) continue;
-    const int ro = r - (dy * w + dx);
-    uint8_t* base = a_taps + tap * A_BLOCK_BYTES + (ro >> 3) * 1024 + (ro & 7) * 128;
-    *reinterpret_cast<uint4*>(base + (((p0) ^ (ro & 7)) << 4)) = lo;
-    *reinterpret_cast<uint4*>(base + (((p0 + 1) ^ (ro & 7)) << 4)) = hi;
-  }
+// 16 columns without waiting: several loads can be in flight before one tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t r[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+
+// Geometry of the tile row owned by an epilogue thread (padded board layout).
+struct RowGeo {
+  int grp, lp, cell, x, y;
+  bool real;  // the row is a board cell of one of the group's ppt positions (not padding)
+};
 
 __device__ __forceinline__ void pack16(const float v[16], uint4& lo, uint4& hi) {
   lo = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
   hi = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
 }
+// 16 channels (16-byte pieces p0, p0 + 1) of buffer row R of a 1024-byte aligned SW128 operand
+__device__ __forceinline__ void store_row16(uint8_t* buf, int R, int p0, uint4 lo, uint4 hi) {
+  uint8_t* base = buf + (R >> 3) * 1024 + (R & 7) * 128;
+  *reinterpret_cast<uint4*>(base + ((p0 ^ (R & 7)) << 4)) = lo;
+  *reinterpret_cast<uint4*>(base + (((p0 + 1) ^ (R & 7)) << 4)) = hi;
+}
+// Descriptor of a [128 x 64] operand that starts `row` rows into a 1024-byte aligned SW128 buffer.
+__device__ __forceinline__ uint64_t desc_rows(uint32_t buf_addr, int row, int mode) {
+  uint64_t d = umma_desc_sw128(buf_addr + (uint32_t)row * 128u);
+  const uint64_t ph = (uint64_t)(row & 7);
+  if (mode == 1) d |= ph << 49;
+  if (mode == 2) d |= ((8 - ph) & 7) << 49;
+  return d;
+}
 
-__global__ void __launch_bounds__(THREADS, 1)
+
+// out[p][j] = act(bias[j] + sum_k wT[k][j] * in[p][k]) for a handful of rows p (J <= 64 outputs, K <= 96,
+// in / out / part in shared memory): the K range is split over EPI_THREADS / J thread groups; a thread
+// first requests all of its <= 48 weights (one L2 round trip instead of one per k), then accumulates 8
+// rows at a time from float4 reads of the inputs; partial sums meet in `part` ([KS][8][J]).
+constexpr int DENSE_MAX_KC = 48;
+__device__ __forceinline__ void dense_small(const float* __restrict__ wT, const float* __restrict__ bias, int K, int J,
+                                            const float* in, int in_stride, int n_rows, float* out, int out_stride,
+                                            bool relu, float* part, int tid) {
+  __builtin_assume(__isShared(in));
+  __builtin_assume(__isShared(out));
+  __builtin_assume(__isShared(part));
+  const int KS = EPI_THREADS / J;
+  const int Kc = (((K + KS - 1) / KS) + 3) & ~3;  // multiple of 4, <= DENSE_MAX_KC
+  const int j = tid % J, kq = tid / J;
+  const int k0 = kq * Kc, k1 = min(K, k0 + Kc);
+  float w[DENSE_MAX_KC];
+#pragma unroll
+  for (int i = 0; i < DENSE_MAX_KC; ++i) w[i] = (kq < KS && k0 + i < k1) ? __ldg(wT + (k0 + i) * J + j) : 0.0f;
+  for (int p0 = 0; p0 < n_rows; p0 += 8) {
+    const int np = min(8, n_rows - p0);
+    if (kq < KS) {
+      float acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.0f;
+      const float* src = in + p0 * in_stride + k0;
+#pragma unroll
+      for (int g = 0; g < DENSE_MAX_KC / 4; ++g) {
+        if (k0 + 4 * g < k1) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 x = *reinterpret_cast<const float4*>(src + (q < np ? q : 0) * in_stride + 4 * g);
+            // weights past k1 are zero; the matching inputs may be stale but are finite
+            acc[q] += w[4 * g] * x.x + w[4 * g + 1] * x.y + w[4 * g + 2] * x.z + w[4 * g + 3] * x.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) part[(kq * 8 + q) * J + j] = acc[q];
+    }
+    epi_barrier();
+    for (int i = tid; i < np * J; i += EPI_THREADS) {
+      const int q = i / J, jj = i - q * J;
+      float a = __ldg(bias + jj);
+      for (int sp = 0; sp < KS; ++sp) a += part[(sp * 8 + q) * J + jj];
+      out[(p0 + q) * out_stride + jj] = relu ? fmaxf(a, 0.0f) : a;
+    }
+    epi_barrier();
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
 cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict__ n_rows_ptr, int n_rows_arg,
                    const ar_game_pod* __restrict__ games, const uint16_t* __restrict__ maze_tab, Params pr,
                    float* __restrict__ out, int* __restrict__ error_flag) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_taps = smem;                                   // 9 x 16 KB im2col image
-  uint8_t* a_aux = smem + 9 * A_BLOCK_BYTES;                // stem input / gpool 1x1 input, [128 x 64]
-  uint8_t* ws = a_aux + A_BLOCK_BYTES;                      // weight ring
-  float* scratch = reinterpret_cast<float*>(ws + N_STAGES * W_STAGE_BYTES);  // [128][32] pool rows; head buffers
-  float* pool_cat = scratch + TILE_M * MAX_G;               // [MAX_PPT][2 * MAX_G]
-  float* pool_out = pool_cat + MAX_PPT * 2 * MAX_G;         // [MAX_PPT][64]
-  Smem* sh = reinterpret_cast<Smem*>(pool_out + MAX_PPT * C);
-  float* vec_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sh) + 128);
+  uint8_t* a_buf = smem;                                    // NG x 20 KB activations (with guard rows)
+  uint8_t* a_aux = a_buf + NG * A_BYTES;                    // NG x 16 KB stem input / gpool 1x1 input; between its
+                                                            // uses: pool rows [128][32] f32, head buffers, partials
+  uint8_t* ws = a_aux + NG * AUX_BYTES;                     // weight ring
+  float* scratch = reinterpret_cast<float*>(a_aux);
+  float* pool_cat = reinterpret_cast<float*>(ws + N_STAGES * W_STAGE_BYTES);  // [NG * MAX_PPT][2 * MAX_G]
+  float* pool_out = pool_cat + NG * MAX_PPT * 2 * MAX_G;    // [NG * MAX_PPT][64]
+  Smem* sh = reinterpret_cast<Smem*>(pool_out + NG * MAX_PPT * C);
+  float* vec_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sh) + 256);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_rows = n_rows_ptr ? (int)*n_rows_ptr : n_rows_arg;
   const int ppt = pr.ppt;
-  const int n_tiles = (n_rows + ppt - 1) / ppt;
+  const int ppc = ppt * NG;  // positions per CTA tile
+  const int n_tiles = (n_rows + ppc - 1) / ppc;
   if ((int)blockIdx.x >= n_tiles) return;
-  const int W = pr.width, Hh = pr.height, S = W * Hh;
+  const int W = pr.width, Hh = pr.height, PW = W + 1, Sp = PW * (Hh + 1);
 
   if (tid == 0) {
     for (int s = 0; s < N_STAGES; ++s) {
       mbar_init(&sh->w_full[s], 1);
       mbar_init(&sh->w_empty[s], 1);
     }
-    mbar_init(&sh->a_ready, 128);
+    mbar_init(&sh->a_ready, EPI_THREADS);
     mbar_init(&sh->mma_done, 1);
     fence_barrier_init();
   }
   if (pr.vec_in_smem)
     for (int i = tid; i < pr.vec_floats; i += THREADS) vec_s[i] = __ldg(pr.vec + i);
   const float* vec = pr.vec_in_smem ? vec_s : pr.vec;
-  // out-of-board taps are never written: zero the im2col image once
-  for (int i = tid; i < 10 * A_BLOCK_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  if (warp == 5) tmem_alloc(&sh->tmem_base, 256);
+  // padding and guard rows are never written: zero the operand buffers once
+  for (int i = tid; i < NG * (A_BYTES + AUX_BYTES) / 16; i += THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == EPI_THREADS / 32 + 1) tmem_alloc(&sh->tmem_base, NG * TMEM_COLS_PER_GROUP);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
-  const uint32_t TX = tmem, TY = tmem + 64, TP = tmem + 128;
+  constexpr uint32_t TX = 0, TY = 64, TP = 128;  // column offsets inside a group's accumulator set
 
-  if (warp == 4) {
+  if (warp == EPI_THREADS / 32) {
     // ================= TMA producer: stem, then per block [pool conv,] conv1 taps, conv2 taps =====
     if (lane == 0) {
       uint32_t it = 0;
@@ -186,62 +264,79 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == EPI_THREADS / 32 + 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
       uint32_t it = 0, a_phase = 0;
       const uint32_t idesc64 = umma_idesc(TILE_M, 64);
-      auto chain = [&](uint32_t d_tmem, const uint8_t* a_block, uint32_t idesc, bool fresh) {
+      const uint32_t a_buf_addr = smem_u32(a_buf), a_aux_addr = smem_u32(a_aux);
+      // one weight stage against both groups; tap < 0: the unshifted auxiliary operand
+      auto chain = [&](uint32_t d_col, int tap, uint32_t idesc, bool fresh) {
         int s = it % N_STAGES;
         uint32_t ph = (it / N_STAGES) & 1;
         mbar_wait(&sh->w_full[s], ph);
         tc_fence_after();
-        uint64_t da = umma_desc_sw128(smem_u32(a_block));
-        uint64_t db = umma_desc_sw128(smem_u32(ws + s * W_STAGE_BYTES));
+        const uint64_t db = umma_desc_sw128(smem_u32(ws + s * W_STAGE_BYTES));
 #pragma unroll
-        for (int k = 0; k < KB / 16; ++k)
-          umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (fresh && k == 0) ? 0u : 1u);
+        for (int g = 0; g < NG; ++g) {
+          uint64_t da;
+          if (tap < 0) {
+            da = umma_desc_sw128(a_aux_addr + g * AUX_BYTES);
+          } else {
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            da = desc_rows(a_buf_addr + g * A_BYTES, GUARD + dy * PW + dx, pr.desc_mode);
+          }
+#pragma unroll
+          for (int k = 0; k < KB / 16; ++k)
+            umma_bf16(tmem + g * TMEM_COLS_PER_GROUP + d_col, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                      (fresh && k == 0) ? 0u : 1u);
+        }
         umma_commit(&sh->w_empty[s]);
         ++it;
       };
       auto wait_a = [&]() { mbar_wait(&sh->a_ready, a_phase); a_phase ^= 1; tc_fence_after(); };
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         wait_a();
-        chain(TX, a_aux, idesc64, true);  // stem
+        chain(TX, -1, idesc64, true);  // stem
         umma_commit(&sh->mma_done);
         for (int b = 0; b < pr.n_blocks; ++b) {
           const int g = pr.blocks[b].gpool;
           wait_a();
-          if (g) chain(TP, a_aux, umma_idesc(TILE_M, g), true);
-          for (int tap = 0; tap < 9; ++tap) chain(TY, a_taps + tap * A_BLOCK_BYTES, idesc64, tap == 0);
+          if (g) chain(TP, -1, umma_idesc(TILE_M, g), true);
+          for (int tap = 0; tap < 9; ++tap) chain(TY, tap, idesc64, tap == 0);
           umma_commit(&sh->mma_done);
           wait_a();
-          for (int tap = 0; tap < 9; ++tap) chain(TX, a_taps + tap * A_BLOCK_BYTES, idesc64, false);  // += residual
+          for (int tap = 0; tap < 9; ++tap) chain(TX, tap, idesc64, false);  // += residual
           umma_commit(&sh->mma_done);
         }
       }
     }
   } else {
-    // ================= encode + epilogues: thread r owns tile row r = TMEM lane r =================
-    const int r = tid;
+    // ========== encode + epilogues: thread (grp, r) owns row r of group grp = TMEM lane r ==========
+    const int r = tid & (TILE_M - 1);
     RowGeo g;
-    g.lp = r / S;
-    g.cell = r - g.lp * S;
-    g.y = g.cell / W;
-    g.x = g.cell - g.y * W;
-    g.in_tile = g.lp < ppt;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    g.grp = tid >> 7;
+    g.lp = r / Sp;
+    const int rem = r - g.lp * Sp;
+    g.y = rem / PW;
+    g.x = rem - g.y * PW;
+    g.cell = g.y * W + g.x;
+    g.real = g.lp < ppt && g.x < W && g.y < Hh;
+    uint8_t* my_buf = a_buf + g.grp * A_BYTES;
+    uint8_t* my_aux = a_aux + g.grp * AUX_BYTES;
+    float* my_scratch = scratch + g.grp * TILE_M * MAX_G;
+    const uint32_t tbase = tmem + g.grp * TMEM_COLS_PER_GROUP + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t done_phase = 0;
     auto wait_mma = [&]() { mbar_wait(&sh->mma_done, done_phase); done_phase ^= 1; tc_fence_after(); };
     auto signal_a = [&]() { tc_fence_before(); fence_proxy_async(); mbar_arrive(&sh->a_ready); };
-    float* feat = scratch;                       // [MAX_PPT][2][64]   (scratch is free after the trunk)
-    float* enc = feat + MAX_PPT * 2 * C;         // [MAX_PPT][2][MAX_P]
-    float* hid = enc + MAX_PPT * 2 * MAX_P;      // [MAX_PPT][2][MAX_H]
-    float* zbuf = hid + MAX_PPT * 2 * MAX_H;     // [MAX_PPT][12]
+    float* catb = scratch;                            // [NG * MAX_PPT][2][CAT]   (a_aux is free after the trunk)
+    float* hid = catb + NG * MAX_PPT * 2 * CAT;       // [NG * MAX_PPT][2][MAX_H]
+    float* head_part = hid + NG * MAX_PPT * 2 * MAX_H;  // dense_small partial sums
+    const int slot = g.grp * ppt + g.lp;              // position slot inside the CTA tile
 
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int pidx = t * ppt + g.lp;
-      const bool live = g.in_tile && pidx < n_rows;
+      const int pidx = t * ppc + slot;
+      const bool live = g.real && pidx < n_rows;
       RowView v;
       const uint16_t* mt = nullptr;
       if (live) {
@@ -276,7 +371,7 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
                                 (uint32_t)e[8 * p + 2] | ((uint32_t)e[8 * p + 3] << 16),
                                 (uint32_t)e[8 * p + 4] | ((uint32_t)e[8 * p + 5] << 16),
                                 (uint32_t)e[8 * p + 6] | ((uint32_t)e[8 * p + 7] << 16));
-          *reinterpret_cast<uint4*>(a_aux + sw128_offset(r, 8 * p)) = pk;
+          *reinterpret_cast<uint4*>(my_aux + sw128_offset(r, 8 * p)) = pk;
         }
       }
       signal_a();
@@ -284,48 +379,52 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
       // ---- trunk.  `stage` = -1: stem result; otherwise the result of block `stage`'s conv2.
       for (int stage = -1; stage < pr.n_blocks; ++stage) {
         if (stage >= 0) {
-          // conv1 (+ pool conv) of block `stage` finished: y = ReLU(Y + b1) -> im2col; pool branch
+          // conv1 (+ pool conv) of block `stage` finished: y = ReLU(Y + b1) -> activation rows; pool branch
           const BlockDesc& bd = pr.blocks[stage];
           wait_mma();
-#pragma unroll 1
+          uint32_t acc[C];  // the whole 64-channel row: four loads in flight, one wait
+#pragma unroll
+          for (int c0 = 0; c0 < C; c0 += 16) tmem_ld16_nowait(tbase + TY + c0, acc + c0);
+          tmem_ld_wait();
+#pragma unroll
           for (int c0 = 0; c0 < C; c0 += 16) {
             float y[16];
-            tmem_ld16(TY + lane_off + c0, y);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j] + vec[64 + stage * VEC_BLOCK + 128 + c0 + j], 0.0f);
+            for (int j = 0; j < 16; ++j)
+              y[j] = fmaxf(__uint_as_float(acc[c0 + j]) + vec[64 + stage * VEC_BLOCK + 128 + c0 + j], 0.0f);
             uint4 lo, hi;
             pack16(y, lo, hi);
-            if (g.in_tile) scatter_taps(a_taps, g, r, W, Hh, c0 >> 3, lo, hi);
+            if (g.real) store_row16(my_buf, GUARD + r, c0 >> 3, lo, hi);
           }
           if (bd.gpool) {
             const int G = bd.gpool;
             for (int c0 = 0; c0 < G; c0 += 16) {
               float p[16];
-              tmem_ld16(TP + lane_off + c0, p);
+              tmem_ld16(tbase + TP + c0, p);
 #pragma unroll
               for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(scratch + r * MAX_G + c0 + j) = make_float4(p[j], p[j + 1], p[j + 2], p[j + 3]);
+                *reinterpret_cast<float4*>(my_scratch + r * MAX_G + ((((c0 + j) >> 2) ^ (r & 7)) << 2)) = make_float4(p[j], p[j + 1], p[j + 2], p[j + 3]);  // 16-byte chunks XOR-swizzled by row: conflict-free
             }
             epi_barrier();
-            for (int i = tid; i < ppt * G; i += 128) {  // mean and max over the board, blocks.py:68-70
-              const int lp = i / G, ch = i - lp * G;
+            for (int i = tid; i < ppc * G; i += EPI_THREADS) {  // mean and max over the board, blocks.py:68-70
+              const int sl = i / G, ch = i - sl * G;
+              const int gq = sl / ppt, lq = sl - gq * ppt;
+              const float* src = scratch + gq * TILE_M * MAX_G;
               float s = 0.0f, m = -INFINITY;
-              for (int c = 0; c < S; ++c) {
-                float x = scratch[(lp * S + c) * MAX_G + ch];
-                s += x;
-                m = fmaxf(m, x);
-              }
-              pool_cat[lp * 2 * MAX_G + ch] = s / (float)S;
-              pool_cat[lp * 2 * MAX_G + G + ch] = m;
+              for (int yy = 0; yy < Hh; ++yy)
+                for (int xx = 0; xx < W; ++xx) {
+                  const int rr = lq * Sp + yy * PW + xx;
+                  float x = src[rr * MAX_G + ((((ch >> 2) ^ (rr & 7)) << 2) | (ch & 3))];
+                  s += x;
+                  m = fmaxf(m, x);
+                }
+              pool_cat[sl * 2 * MAX_G + ch] = s / (float)(W * Hh);
+              pool_cat[sl * 2 * MAX_G + G + ch] = m;
             }
             epi_barrier();
-            for (int i = tid; i < ppt * C; i += 128) {  // pool_linear, blocks.py:72
-              const int lp = i >> 6, c = i & 63;
-              float acc = __ldg(bd.lin_b + c);
-              for (int j = 0; j < 2 * G; ++j) acc += __ldg(bd.lin_wT + j * C + c) * pool_cat[lp * 2 * MAX_G + j];
-              pool_out[lp * C + c] = acc;
-            }
-            epi_barrier();
+            // pool_linear, blocks.py:72 (a_aux is free between the pool conv and the next block's input)
+            dense_small(bd.lin_wT, bd.lin_b, 2 * G, C, pool_cat, 2 * MAX_G, ppc, pool_out, C, false,
+                        reinterpret_cast<float*>(a_aux), tid);
           }
           signal_a();
         }
@@ -336,110 +435,120 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
         const bool last = stage + 1 == pr.n_blocks;
         const BlockDesc* nb = last ? nullptr : &pr.blocks[stage + 1];
         const float* nv = vec + 64 + (stage + 1) * VEC_BLOCK;  // the next block's pre-activation vectors
-#pragma unroll 1
+        uint32_t xacc[C];
+#pragma unroll
+        for (int c0 = 0; c0 < C; c0 += 16) tmem_ld16_nowait(tbase + TX + c0, xacc + c0);
+        tmem_ld_wait();
+#pragma unroll
         for (int c0 = 0; c0 < C; c0 += 16) {
           float x[16];
-          tmem_ld16(TX + lane_off + c0, x);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(xacc[c0 + j]);
           if (is_stem) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j] + vec[c0 + j], 0.0f);
           }
-          if (add_pool && g.in_tile) {
+          if (add_pool && g.real) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] += pool_out[g.lp * C + c0 + j];
+            for (int j = 0; j < 16; ++j) x[j] += pool_out[slot * C + c0 + j];
           }
-          if ((is_stem || add_pool) && !last) tmem_st16(TX + lane_off + c0, x);
+          if ((is_stem || add_pool) && !last) tmem_st16(tbase + TX + c0, x);
           if (!last) {
             float a[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) a[j] = fmaxf(x[j] * nv[c0 + j] + nv[64 + c0 + j], 0.0f);
             uint4 lo, hi;
             pack16(a, lo, hi);
-            if (g.in_tile) scatter_taps(a_taps, g, r, W, Hh, c0 >> 3, lo, hi);
+            if (g.real) store_row16(my_buf, GUARD + r, c0 >> 3, lo, hi);
             if (nb->gpool) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) a[j] = fmaxf(x[j] * nv[192 + c0 + j] + nv[256 + c0 + j], 0.0f);
               pack16(a, lo, hi);
-              *reinterpret_cast<uint4*>(a_aux + sw128_offset(r, c0)) = lo;
-              *reinterpret_cast<uint4*>(a_aux + sw128_offset(r, c0 + 8)) = hi;
+              *reinterpret_cast<uint4*>(my_aux + sw128_offset(r, c0)) = lo;
+              *reinterpret_cast<uint4*>(my_aux + sw128_offset(r, c0 + 8)) = hi;
             }
           } else if (live) {
             // trunk finished: features at the players' cells (mask-multiply-sum, model.py:187-190)
             if (g.cell == v.p1)
 #pragma unroll
-              for (int j = 0; j < 16; ++j) feat[(g.lp * 2 + 0) * C + c0 + j] = x[j];
+              for (int j = 0; j < 16; ++j) catb[(slot * 2 + 0) * CAT + c0 + j] = x[j];
             if (g.cell == v.p2)
 #pragma unroll
-              for (int j = 0; j < 16; ++j) feat[(g.lp * 2 + 1) * C + c0 + j] = x[j];
+              for (int j = 0; j < 16; ++j) catb[(slot * 2 + 1) * CAT + c0 + j] = x[j];
           }
         }
         if (!last) signal_a();
       }
       tc_fence_before();
 
-      // ---- DeepSet heads on CUDA cores (model.py:192-213)
+      // ---- DeepSet heads on CUDA cores (model.py:192-213); slot sl -> position t * ppc + sl
       const int P = pr.P, H = pr.H;
-      const int n_pos = min(ppt, n_rows - t * ppt);
-      for (int i = tid; i < n_pos * 2 * P; i += 128) {
-        const int j = i % P, pl = (i / P) & 1, lp = i / (2 * P);
-        RowView q = row_view(rows[t * ppt + lp], games);
+      const int n_pos = min(ppc, n_rows - t * ppc);
+      for (int i = tid; i < n_pos * 2 * P; i += EPI_THREADS) {
+        const int j = i % P, pl = (i / P) & 1, sl = i / (2 * P);
+        RowView q = row_view(rows[t * ppc + sl], games);
         const float side0 = (pl ? q.s2 : q.s1) / 10.0f, side1 = (float)(pl ? q.mud2 : q.mud1) / 10.0f, side2 = q.progress;
         float acc = __ldg(pr.enc_b + j) + __ldg(pr.enc_w + j * 3) * side0 + __ldg(pr.enc_w + j * 3 + 1) * side1 +
                     __ldg(pr.enc_w + j * 3 + 2) * side2;
-        enc[(lp * 2 + pl) * MAX_P + j] = fmaxf(acc, 0.0f);
+        catb[(sl * 2 + pl) * CAT + C + j] = fmaxf(acc, 0.0f);
       }
+      for (int i = tid; i < n_pos * 2 * (MAX_P - P); i += EPI_THREADS)  // the buffer held operand bits: finite padding
+        catb[(i / (MAX_P - P)) * CAT + C + P + i % (MAX_P - P)] = 0.0f;
       epi_barrier();
-      for (int i = tid; i < n_pos * 2 * H; i += 128) {
-        const int j = i % H, pl = (i / H) & 1, lp = i / (2 * H);
-        const float* f = feat + (lp * 2 + pl) * C;
-        const float* e = enc + (lp * 2 + pl) * MAX_P;
-        float acc = __ldg(pr.comb_b + j);
-        for (int k = 0; k < C; ++k) acc += __ldg(pr.comb_wT + k * H + j) * f[k];
-        for (int k = 0; k < P; ++k) acc += __ldg(pr.comb_wT + (C + k) * H + j) * e[k];
-        hid[(lp * 2 + pl) * MAX_H + j] = fmaxf(acc, 0.0f);
-      }
-      epi_barrier();
-      for (int i = tid; i < n_pos * 12; i += 128) {
-        const int a = i % 6, pl = (i / 6) & 1, lp = i / 12;
-        const float* hi_ = hid + (lp * 2 + pl) * MAX_H;
-        const float* ho = hid + (lp * 2 + (pl ^ 1)) * MAX_H;
-        const float* wr = pr.head_w + a * 2 * H;
-        float acc = __ldg(pr.head_b + a);
-        for (int k = 0; k < H; ++k) acc += __ldg(wr + k) * hi_[k] + __ldg(wr + H + k) * (hi_[k] + ho[k]);
-        zbuf[lp * 12 + pl * 6 + a] = acc;
-      }
-      epi_barrier();
-      if (tid < n_pos) {
-        const float* z = zbuf + tid * 12;
-        float o[12];
+      // combiner: h_i = ReLU(Linear(C + P, H)(cat(f_i, e_i)))
+      dense_small(pr.comb_wT, pr.comb_b, C + P, H, catb, CAT, n_pos * 2, hid, MAX_H, true, head_part, tid);
+      // policy / value heads on cat(h_i, h_1 + h_2): one warp per position, lanes over the hidden units
+      for (int sl = warp; sl < n_pos; sl += EPI_THREADS / 32) {
+        float z[12];
 #pragma unroll
-        for (int pl = 0; pl < 2; ++pl) {
-          float m = z[pl * 6];
+        for (int i = 0; i < 12; ++i) z[i] = 0.0f;
+        for (int k = lane; k < H; k += 32) {
+          const float h0 = hid[(sl * 2 + 0) * MAX_H + k], h1 = hid[(sl * 2 + 1) * MAX_H + k], hs = h0 + h1;
 #pragma unroll
-          for (int j = 1; j < 5; ++j) m = fmaxf(m, z[pl * 6 + j]);
-          float e[5], s = 0.0f;
-#pragma unroll
-          for (int j = 0; j < 5; ++j) { e[j] = expf(z[pl * 6 + j] - m); s += e[j]; }
-#pragma unroll
-          for (int j = 0; j < 5; ++j) o[pl * 5 + j] = e[j] / s;
-          float x = z[pl * 6 + 5];
-          o[10 + pl] = x > 20.0f ? x : log1pf(expf(x));
+          for (int a = 0; a < 6; ++a) {
+            const float wa = __ldg(pr.head_w + a * 2 * H + k), wb = __ldg(pr.head_w + a * 2 * H + H + k);
+            z[a] += wa * h0 + wb * hs;
+            z[6 + a] += wa * h1 + wb * hs;
+          }
         }
-        bool ok = true;
 #pragma unroll
-        for (int j = 0; j < 12; ++j) ok = ok && isfinite(o[j]);
-        if (!ok) atomicCAS(error_flag, 0, (int)AR_ERR_NONFINITE);
-        float4* dst = reinterpret_cast<float4*>(out + (size_t)(t * ppt + tid) * 12);
-        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-        dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+        for (int i = 0; i < 12; ++i) {
+#pragma unroll
+          for (int sh = 16; sh > 0; sh >>= 1) z[i] += __shfl_xor_sync(0xffffffffu, z[i], sh);
+        }
+        if (lane == 0) {
+          float o[12];
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) z[pl * 6 + a] += __ldg(pr.head_b + a);
+            float m = z[pl * 6];
+#pragma unroll
+            for (int j = 1; j < 5; ++j) m = fmaxf(m, z[pl * 6 + j]);
+            float e[5], sum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) { e[j] = expf(z[pl * 6 + j] - m); sum += e[j]; }
+#pragma unroll
+            for (int j = 0; j < 5; ++j) o[pl * 5 + j] = e[j] / sum;
+            float x = z[pl * 6 + 5];
+            o[10 + pl] = x > 20.0f ? x : log1pf(expf(x));
+          }
+          bool ok = true;
+#pragma unroll
+          for (int j = 0; j < 12; ++j) ok = ok && isfinite(o[j]);
+          if (!ok) atomicCAS(error_flag, 0, (int)AR_ERR_NONFINITE);
+          float4* dst = reinterpret_cast<float4*>(out + (size_t)(t * ppc + sl) * 12);
+          dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+          dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+          dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+        }
       }
       epi_barrier();  // scratch is reused by the next tile
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 256);
+  if (warp == EPI_THREADS / 32 + 1) tmem_dealloc(tmem, NG * TMEM_COLS_PER_GROUP);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -501,8 +610,8 @@ struct Model : LeafEvaluator {
       err = "the fused CNN kernel needs a 3x3 stem with 5 input and 64 output channels";
       return AR_ERR_UNSUPPORTED;
     }
-    int ppt = TILE_M / S;
-    if (ppt < 1) { err = "board too large for the fused CNN kernel"; return AR_ERR_UNSUPPORTED; }
+    int ppt = TILE_M / ((width + 1) * (height + 1));  // padded board rows per position
+    if (ppt < 1 || width + 2 > GUARD) { err = "board too large for the fused CNN kernel"; return AR_ERR_UNSUPPORTED; }
     if (ppt > MAX_PPT) ppt = MAX_PPT;
     const ar_tensor_desc* ew = find_tensor(t, n, "player_encoder.0.weight");
     const ar_tensor_desc* cw = find_tensor(t, n, "combiner.0.weight");
@@ -630,9 +739,11 @@ struct Model : LeafEvaluator {
     pr.enc_w = dfl + o_encw; pr.enc_b = dfl + o_encb;
     pr.comb_wT = dfl + o_combw; pr.comb_b = dfl + o_combb;
     pr.head_w = dfl + o_headw; pr.head_b = dfl + o_headb;
-    smem_bytes = (size_t)10 * A_BLOCK_BYTES + N_STAGES * W_STAGE_BYTES + (size_t)TILE_M * MAX_G * 4 +
-                 (size_t)MAX_PPT * 2 * MAX_G * 4 + (size_t)MAX_PPT * C * 4 + 128 + 1024;
-    pr.vec_in_smem = smem_bytes + vecs.size() * 4 <= 227 * 1024 ? 1 : 0;
+    smem_bytes = (size_t)NG * (A_BYTES + AUX_BYTES) + N_STAGES * W_STAGE_BYTES +
+                 (size_t)NG * MAX_PPT * 2 * MAX_G * 4 + (size_t)NG * MAX_PPT * C * 4 + 256 + 1024;
+    if (const char* m = getenv("AR_CNN_DESC_MODE")) pr.desc_mode = atoi(m);
+    const size_t smem_limit = (size_t)228 * 1024 / CTAS_PER_SM - 1024;  // per CTA, CTAS_PER_SM resident
+    pr.vec_in_smem = smem_bytes + vecs.size() * 4 <= smem_limit ? 1 : 0;
     if (pr.vec_in_smem) smem_bytes += vecs.size() * 4;
     CKN(cudaFuncSetAttribute(cnn_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     int dev = 0;
@@ -645,8 +756,8 @@ struct Model : LeafEvaluator {
   cudaError_t forward(const EvalRow* rows, const uint32_t* n_rows_dev, int n_rows_max, const ar_game_pod* games,
                       const uint16_t* maze_tab, float* out, int* error_flag, cudaStream_t stream) const override {
     if (n_rows_max <= 0) return cudaSuccess;
-    int tiles = (n_rows_max + pr.ppt - 1) / pr.ppt;
-    int grid = tiles < n_sms ? tiles : n_sms;
+    int tiles = (n_rows_max + pr.ppt * NG - 1) / (pr.ppt * NG);
+    int grid = tiles < n_sms * CTAS_PER_SM ? tiles : n_sms * CTAS_PER_SM;
     cnn_forward_kernel<<<grid, THREADS, smem_bytes, stream>>>(rows, n_rows_dev, n_rows_max, games, maze_tab, pr, out,
                                                               error_flag);
     return cudaGetLastError();
