@@ -19,14 +19,15 @@
 // start address is shifted by whole rows (the swizzle is a function of the shared-memory address, and
 // the buffer is written with the same address-based swizzle).  An epilogue thread therefore stores
 // its 128-byte activation vector once instead of nine times, and out-of-board taps read the padding.
-// A CTA owns NG = 2 such 128-row groups (two TMEM accumulator sets) that share every weight stage, so
-// each 8 KB weight tap streamed by the TMA bulk-copy ring feeds 2 x 4 MMAs and 8 epilogue warps.
+// A pipeline (one 128-row tile at a time: encode -> MMA -> epilogue -> MMA ...) is a serial chain, so two
+// CTAs share an SM (NG = 1: 113 KB of shared memory and 256 TMEM columns each) and one CTA's epilogue
+// overlaps the other's MMAs; a pipeline has 8 epilogue warps (two threads per tile row, 32 channels each),
+// a TMA warp streaming 8 KB weight taps through an 8-stage bulk-copy ring and an MMA warp that stays
+// converged (descriptors in uniform registers, tcgen05 instructions predicated on lane 0).
 // The residual stream never leaves TMEM: conv2 accumulates straight onto it (accumulate = 1 from
 // the first MMA), conv1 goes to a second accumulator, the gpool 1x1 convolution to a third.
 // BatchNorms that follow a convolution are folded into its weights; pre-activation BatchNorms are
 // applied in the epilogue.  The tiny per-player head (3 -> P -> H -> 6) runs on CUDA cores.
-#include <cstdlib>
-
 #include "nn_common.cuh"
 
 namespace ar {
@@ -37,15 +38,16 @@ constexpr int C = 64;
 #ifndef AR_CNN_NG
 #define AR_CNN_NG 1
 #endif
-constexpr int NG = AR_CNN_NG;                    // 128-row groups per CTA (1: two CTAs share an SM)
+constexpr int NG = AR_CNN_NG;                    // independent 128-row pipelines per CTA (1: two CTAs share an SM)
 constexpr int CTAS_PER_SM = NG == 1 ? 2 : 1;
-constexpr int EPI_THREADS = TILE_M * NG;
+constexpr int GT = 2 * TILE_M;                   // epilogue threads of one pipeline: two per tile row (32 channels each)
+constexpr int EPI_THREADS = GT * NG;
 constexpr int THREADS = EPI_THREADS + 64;        // + TMA warp + MMA warp
 constexpr int GUARD = 16;                        // zero rows before / after a group's activation rows
 constexpr int A_BYTES = (TILE_M + 2 * GUARD) * 128;  // 20 KB activation buffer of one group
 constexpr int AUX_BYTES = TILE_M * KB * 2;       // 16 KB: stem input / gpool 1x1 input of one group
 constexpr int W_STAGE_BYTES = C * KB * 2;        // 8 KB: one tap of one convolution
-constexpr int N_STAGES = NG == 1 ? 8 : 14;      // a 3x3 convolution is 9 stages
+constexpr int N_STAGES = NG == 1 ? 8 : 16;      // a 3x3 convolution is 9 stages
 constexpr int MAX_BLOCKS = 16;
 constexpr int MAX_PPT = 8;                       // positions per group
 constexpr int MAX_G = 32;                        // gpool channels
@@ -85,15 +87,14 @@ struct Params {
   const float* vec;
   int vec_floats;          // 64 + 320 * n_blocks
   int vec_in_smem;         // staged (fits next to the operand buffers) or read through L1
-  int desc_mode;           // descriptor base-offset convention for row-shifted operands (0 = none)
 };
 constexpr int VEC_BLOCK = 320;
 
 struct Smem {
   uint64_t w_full[N_STAGES];
   uint64_t w_empty[N_STAGES];
-  uint64_t a_ready;
-  uint64_t mma_done;
+  uint64_t a_ready[NG];
+  uint64_t mma_done[NG];
   uint32_t tmem_base;
 };
 
@@ -118,7 +119,8 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t r[16])
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+// named barrier of pipeline `grp` (its GT epilogue threads)
+__device__ __forceinline__ void grp_barrier(int grp) { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(GT) : "memory"); }
 
 // Geometry of the tile row owned by an epilogue thread (padded board layout).
 struct RowGeo {
@@ -136,63 +138,61 @@ __device__ __forceinline__ void store_row16(uint8_t* buf, int R, int p0, uint4 l
   *reinterpret_cast<uint4*>(base + ((p0 ^ (R & 7)) << 4)) = lo;
   *reinterpret_cast<uint4*>(base + (((p0 + 1) ^ (R & 7)) << 4)) = hi;
 }
-// Descriptor of a [128 x 64] operand that starts `row` rows into a 1024-byte aligned SW128 buffer.
-__device__ __forceinline__ uint64_t desc_rows(uint32_t buf_addr, int row, int mode) {
-  uint64_t d = umma_desc_sw128(buf_addr + (uint32_t)row * 128u);
-  const uint64_t ph = (uint64_t)(row & 7);
-  if (mode == 1) d |= ph << 49;
-  if (mode == 2) d |= ((8 - ph) & 7) << 49;
-  return d;
+// Descriptor of a [128 x 64] operand that starts `row` rows into a 1024-byte aligned SW128 buffer: the
+// hardware applies the 128B swizzle to the shared-memory address, so a start address shifted by whole rows
+// reads rows row .. row+127 as they were written (base-offset field 0; checked on B200 by the parity tests).
+__device__ __forceinline__ uint64_t desc_rows(uint32_t buf_addr, int row) {
+  return umma_desc_sw128(buf_addr + (uint32_t)row * 128u);
 }
 
-
 // out[p][j] = act(bias[j] + sum_k wT[k][j] * in[p][k]) for a handful of rows p (J <= 64 outputs, K <= 96,
-// in / out / part in shared memory): the K range is split over EPI_THREADS / J thread groups; a thread
-// first requests all of its <= 48 weights (one L2 round trip instead of one per k), then accumulates 8
-// rows at a time from float4 reads of the inputs; partial sums meet in `part` ([KS][8][J]).
-constexpr int DENSE_MAX_KC = 48;
+// in / out / part in shared memory): the K range is split over GT / J thread groups; a thread
+// first requests all of its <= 24 weights (one L2 round trip instead of one per k), then accumulates DENSE_RB
+// rows at a time from float4 reads of the inputs; partial sums meet in `part` ([KS][DENSE_RB][J]).
+constexpr int DENSE_MAX_KC = 24;  // K <= 96 over GT / J >= 4 thread groups
+constexpr int DENSE_RB = 4;       // rows per pass (7x7: 2 positions x 2 players = one pass)
 __device__ __forceinline__ void dense_small(const float* __restrict__ wT, const float* __restrict__ bias, int K, int J,
                                             const float* in, int in_stride, int n_rows, float* out, int out_stride,
-                                            bool relu, float* part, int tid) {
+                                            bool relu, float* part, int tid, int grp) {
   __builtin_assume(__isShared(in));
   __builtin_assume(__isShared(out));
   __builtin_assume(__isShared(part));
-  const int KS = EPI_THREADS / J;
+  const int KS = GT / J;
   const int Kc = (((K + KS - 1) / KS) + 3) & ~3;  // multiple of 4, <= DENSE_MAX_KC
   const int j = tid % J, kq = tid / J;
   const int k0 = kq * Kc, k1 = min(K, k0 + Kc);
   float w[DENSE_MAX_KC];
 #pragma unroll
   for (int i = 0; i < DENSE_MAX_KC; ++i) w[i] = (kq < KS && k0 + i < k1) ? __ldg(wT + (k0 + i) * J + j) : 0.0f;
-  for (int p0 = 0; p0 < n_rows; p0 += 8) {
-    const int np = min(8, n_rows - p0);
+  for (int p0 = 0; p0 < n_rows; p0 += DENSE_RB) {
+    const int np = min(DENSE_RB, n_rows - p0);
     if (kq < KS) {
-      float acc[8];
+      float acc[DENSE_RB];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] = 0.0f;
+      for (int q = 0; q < DENSE_RB; ++q) acc[q] = 0.0f;
       const float* src = in + p0 * in_stride + k0;
 #pragma unroll
       for (int g = 0; g < DENSE_MAX_KC / 4; ++g) {
         if (k0 + 4 * g < k1) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < DENSE_RB; ++q) {
             const float4 x = *reinterpret_cast<const float4*>(src + (q < np ? q : 0) * in_stride + 4 * g);
-            // weights past k1 are zero; the matching inputs may be stale but are finite
+            // weights past k1 are zero; the matching inputs are zero-filled or finite
             acc[q] += w[4 * g] * x.x + w[4 * g + 1] * x.y + w[4 * g + 2] * x.z + w[4 * g + 3] * x.w;
           }
         }
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) part[(kq * 8 + q) * J + j] = acc[q];
+      for (int q = 0; q < DENSE_RB; ++q) part[(kq * DENSE_RB + q) * J + j] = acc[q];
     }
-    epi_barrier();
-    for (int i = tid; i < np * J; i += EPI_THREADS) {
+    grp_barrier(grp);
+    for (int i = tid; i < np * J; i += GT) {
       const int q = i / J, jj = i - q * J;
       float a = __ldg(bias + jj);
-      for (int sp = 0; sp < KS; ++sp) a += part[(sp * 8 + q) * J + jj];
+      for (int sp = 0; sp < KS; ++sp) a += part[(sp * DENSE_RB + q) * J + jj];
       out[(p0 + q) * out_stride + jj] = relu ? fmaxf(a, 0.0f) : a;
     }
-    epi_barrier();
+    grp_barrier(grp);
   }
 }
 
@@ -206,27 +206,32 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
   uint8_t* a_aux = a_buf + NG * A_BYTES;                    // NG x 16 KB stem input / gpool 1x1 input; between its
                                                             // uses: pool rows [128][32] f32, head buffers, partials
   uint8_t* ws = a_aux + NG * AUX_BYTES;                     // weight ring
-  float* scratch = reinterpret_cast<float*>(a_aux);
   float* pool_cat = reinterpret_cast<float*>(ws + N_STAGES * W_STAGE_BYTES);  // [NG * MAX_PPT][2 * MAX_G]
   float* pool_out = pool_cat + NG * MAX_PPT * 2 * MAX_G;    // [NG * MAX_PPT][64]
   Smem* sh = reinterpret_cast<Smem*>(pool_out + NG * MAX_PPT * C);
-  float* vec_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sh) + 256);
+  static_assert(sizeof(Smem) <= 512, "barrier block");
+  float* vec_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sh) + 512);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_rows = n_rows_ptr ? (int)*n_rows_ptr : n_rows_arg;
   const int ppt = pr.ppt;
-  const int ppc = ppt * NG;  // positions per CTA tile
-  const int n_tiles = (n_rows + ppc - 1) / ppc;
-  if ((int)blockIdx.x >= n_tiles) return;
+  const int n_tiles = (n_rows + ppt - 1) / ppt;  // one tile = ppt positions = one pass of one pipeline
+  if ((int)blockIdx.x * NG >= n_tiles) return;
   const int W = pr.width, Hh = pr.height, PW = W + 1, Sp = PW * (Hh + 1);
+  // Round i gives pipeline g of this CTA the tile (i * gridDim.x + blockIdx.x) * NG + g.  The producer and
+  // the MMA issuer walk the same job order: for each round, for each job (stem, then per block conv1
+  // [+ pool conv] and conv2), for each pipeline that has a tile in this round.
+  const int tile_stride = (int)gridDim.x * NG, tile0 = (int)blockIdx.x * NG;
 
   if (tid == 0) {
     for (int s = 0; s < N_STAGES; ++s) {
       mbar_init(&sh->w_full[s], 1);
       mbar_init(&sh->w_empty[s], 1);
     }
-    mbar_init(&sh->a_ready, EPI_THREADS);
-    mbar_init(&sh->mma_done, 1);
+    for (int g = 0; g < NG; ++g) {
+      mbar_init(&sh->a_ready[g], GT / 32);
+      mbar_init(&sh->mma_done[g], 1);
+    }
     fence_barrier_init();
   }
   if (pr.vec_in_smem)
@@ -240,10 +245,10 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
-  constexpr uint32_t TX = 0, TY = 64, TP = 128;  // column offsets inside a group's accumulator set
+  constexpr uint32_t TX = 0, TY = 64, TP = 128;  // column offsets inside a pipeline's accumulator set
 
   if (warp == EPI_THREADS / 32) {
-    // ================= TMA producer: stem, then per block [pool conv,] conv1 taps, conv2 taps =====
+    // ================= TMA producer =================
     if (lane == 0) {
       uint32_t it = 0;
       auto push = [&](const uint8_t* src, uint32_t bytes) {
@@ -254,88 +259,110 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
         tma_bulk_g2s(ws + s * W_STAGE_BYTES, src, bytes, &sh->w_full[s]);
         ++it;
       };
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        push(pr.w_stem, W_STAGE_BYTES);
+      for (int t0 = tile0; t0 < n_tiles; t0 += tile_stride) {
+        const int ng = min(NG, n_tiles - t0);
+        for (int g = 0; g < ng; ++g) push(pr.w_stem, W_STAGE_BYTES);
         for (int b = 0; b < pr.n_blocks; ++b) {
           const BlockDesc& bd = pr.blocks[b];
-          if (bd.gpool) push(bd.w_pool, (uint32_t)bd.gpool * KB * 2);
-          for (int tap = 0; tap < 9; ++tap) push(bd.w1 + (size_t)tap * W_STAGE_BYTES, W_STAGE_BYTES);
-          for (int tap = 0; tap < 9; ++tap) push(bd.w2 + (size_t)tap * W_STAGE_BYTES, W_STAGE_BYTES);
+          for (int g = 0; g < ng; ++g) {
+            if (bd.gpool) push(bd.w_pool, (uint32_t)bd.gpool * KB * 2);
+            for (int tap = 0; tap < 9; ++tap) push(bd.w1 + (size_t)tap * W_STAGE_BYTES, W_STAGE_BYTES);
+          }
+          for (int g = 0; g < ng; ++g)
+            for (int tap = 0; tap < 9; ++tap) push(bd.w2 + (size_t)tap * W_STAGE_BYTES, W_STAGE_BYTES);
         }
       }
     }
   } else if (warp == EPI_THREADS / 32 + 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      uint32_t it = 0, a_phase = 0;
+    // The whole warp walks the job list converged (every operand stays warp-uniform, so the descriptors live
+    // in uniform registers); the tcgen05 instructions themselves are predicated on lane 0.
+    {
+      const uint32_t issue = lane == 0 ? 1u : 0u;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);  // provably warp-uniform
+      uint32_t it = 0, a_phase[NG];
+      for (int g = 0; g < NG; ++g) a_phase[g] = 0;
       const uint32_t idesc64 = umma_idesc(TILE_M, 64);
-      const uint32_t a_buf_addr = smem_u32(a_buf), a_aux_addr = smem_u32(a_aux);
-      // one weight stage against both groups; tap < 0: the unshifted auxiliary operand
-      auto chain = [&](uint32_t d_col, int tap, uint32_t idesc, bool fresh) {
-        int s = it % N_STAGES;
-        uint32_t ph = (it / N_STAGES) & 1;
-        mbar_wait(&sh->w_full[s], ph);
-        tc_fence_after();
-        const uint64_t db = umma_desc_sw128(smem_u32(ws + s * W_STAGE_BYTES));
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          uint64_t da;
-          if (tap < 0) {
-            da = umma_desc_sw128(a_aux_addr + g * AUX_BYTES);
-          } else {
-            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-            da = desc_rows(a_buf_addr + g * A_BYTES, GUARD + dy * PW + dx, pr.desc_mode);
-          }
-#pragma unroll
-          for (int k = 0; k < KB / 16; ++k)
-            umma_bf16(tmem + g * TMEM_COLS_PER_GROUP + d_col, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                      (fresh && k == 0) ? 0u : 1u);
+      const uint64_t w_desc0 = umma_desc_sw128(smem_u32(ws));
+      // one weight stage against pipeline g; tap < 0: the unshifted auxiliary operand
+      auto chain = [&](int g, uint32_t d_col, int tap, uint32_t idesc, bool fresh) {
+        const int s = __shfl_sync(0xffffffffu, it % N_STAGES, 0);
+        const uint32_t ph = (it / N_STAGES) & 1;
+        mbar_wait_warp(&sh->w_full[s], ph);
+        const uint64_t db = w_desc0 + (uint64_t)(s * (W_STAGE_BYTES >> 4));
+        uint64_t da;
+        if (tap < 0) {
+          da = umma_desc_sw128(smem_u32(a_aux) + g * AUX_BYTES);
+        } else {
+          const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+          da = desc_rows(smem_u32(a_buf) + g * A_BYTES, GUARD + dy * PW + dx);
         }
-        umma_commit(&sh->w_empty[s]);
+        const uint32_t d = tmem_u + g * TMEM_COLS_PER_GROUP + d_col;
+        umma_bf16_pred(d, da, db, idesc, fresh ? 0u : 1u, issue);
+#pragma unroll
+        for (int k = 1; k < KB / 16; ++k) umma_bf16_pred(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u, issue);
+        umma_commit_pred(&sh->w_empty[s], issue);
         ++it;
       };
-      auto wait_a = [&]() { mbar_wait(&sh->a_ready, a_phase); a_phase ^= 1; tc_fence_after(); };
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        wait_a();
-        chain(TX, -1, idesc64, true);  // stem
-        umma_commit(&sh->mma_done);
+      auto wait_a = [&](int g) { mbar_wait_warp(&sh->a_ready[g], a_phase[g]); a_phase[g] ^= 1; tc_fence_after(); };
+      for (int t0 = tile0; t0 < n_tiles; t0 += tile_stride) {
+        const int ng = min(NG, n_tiles - t0);
+        for (int g = 0; g < ng; ++g) {
+          wait_a(g);
+          chain(g, TX, -1, idesc64, true);  // stem
+          umma_commit_pred(&sh->mma_done[g], issue);
+        }
         for (int b = 0; b < pr.n_blocks; ++b) {
-          const int g = pr.blocks[b].gpool;
-          wait_a();
-          if (g) chain(TP, -1, umma_idesc(TILE_M, g), true);
-          for (int tap = 0; tap < 9; ++tap) chain(TY, tap, idesc64, tap == 0);
-          umma_commit(&sh->mma_done);
-          wait_a();
-          for (int tap = 0; tap < 9; ++tap) chain(TX, tap, idesc64, false);  // += residual
-          umma_commit(&sh->mma_done);
+          const int gp = pr.blocks[b].gpool;
+          for (int g = 0; g < ng; ++g) {
+            wait_a(g);
+            if (gp) chain(g, TP, -1, umma_idesc(TILE_M, gp), true);
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) chain(g, TY, tap, idesc64, tap == 0);
+            umma_commit_pred(&sh->mma_done[g], issue);
+          }
+          for (int g = 0; g < ng; ++g) {
+            wait_a(g);
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) chain(g, TX, tap, idesc64, false);  // += residual
+            umma_commit_pred(&sh->mma_done[g], issue);
+          }
         }
       }
+      __syncwarp();
     }
   } else {
-    // ========== encode + epilogues: thread (grp, r) owns row r of group grp = TMEM lane r ==========
-    const int r = tid & (TILE_M - 1);
+    // ==== encode + epilogues: pipeline grp; threads r and r + 128 own tile row r = TMEM lane r, 32 channels each ====
+    const int grp = tid / GT, q = tid - grp * GT, r = q & (TILE_M - 1), half = q >> 7;
     RowGeo g;
-    g.grp = tid >> 7;
     g.lp = r / Sp;
     const int rem = r - g.lp * Sp;
     g.y = rem / PW;
     g.x = rem - g.y * PW;
     g.cell = g.y * W + g.x;
     g.real = g.lp < ppt && g.x < W && g.y < Hh;
-    uint8_t* my_buf = a_buf + g.grp * A_BYTES;
-    uint8_t* my_aux = a_aux + g.grp * AUX_BYTES;
-    float* my_scratch = scratch + g.grp * TILE_M * MAX_G;
-    const uint32_t tbase = tmem + g.grp * TMEM_COLS_PER_GROUP + ((uint32_t)((warp & 3) * 32) << 16);
+    uint8_t* my_buf = a_buf + grp * A_BYTES;
+    uint8_t* my_aux = a_aux + grp * AUX_BYTES;
+    float* scratch = reinterpret_cast<float*>(my_aux);  // pool rows [128][32] f32 between the operand's uses
+    float* pcat = pool_cat + grp * MAX_PPT * 2 * MAX_G;
+    float* pout = pool_out + grp * MAX_PPT * C;
+    const uint32_t tbase = tmem + grp * TMEM_COLS_PER_GROUP + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t done_phase = 0;
-    auto wait_mma = [&]() { mbar_wait(&sh->mma_done, done_phase); done_phase ^= 1; tc_fence_after(); };
-    auto signal_a = [&]() { tc_fence_before(); fence_proxy_async(); mbar_arrive(&sh->a_ready); };
-    float* catb = scratch;                            // [NG * MAX_PPT][2][CAT]   (a_aux is free after the trunk)
-    float* hid = catb + NG * MAX_PPT * 2 * CAT;       // [NG * MAX_PPT][2][MAX_H]
-    float* head_part = hid + NG * MAX_PPT * 2 * MAX_H;  // dense_small partial sums
-    const int slot = g.grp * ppt + g.lp;              // position slot inside the CTA tile
+    auto wait_mma = [&]() { mbar_wait(&sh->mma_done[grp], done_phase); done_phase ^= 1; tc_fence_after(); };
+    // every thread orders its generic-proxy stores before the async proxy, one lane per warp arrives
+    auto signal_a = [&]() {
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->a_ready[grp]);
+    };
+    float* catb = scratch;                       // [MAX_PPT][2][CAT]   (the operand buffer is free after the trunk)
+    float* hid = catb + MAX_PPT * 2 * CAT;       // [MAX_PPT][2][MAX_H]
+    float* head_part = hid + MAX_PPT * 2 * MAX_H;  // dense_small partial sums (<= GT * DENSE_RB floats)
+    static_assert((MAX_PPT * 2 * (CAT + MAX_H) + GT * DENSE_RB) * 4 <= AUX_BYTES, "head buffers fit the operand buffer");
 
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int pidx = t * ppc + slot;
+    for (int t = tile0 + grp; t < n_tiles; t += tile_stride) {
+      const int pidx = t * ppt + g.lp;
       const bool live = g.real && pidx < n_rows;
       RowView v;
       const uint16_t* mt = nullptr;
@@ -371,7 +398,7 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
                                 (uint32_t)e[8 * p + 2] | ((uint32_t)e[8 * p + 3] << 16),
                                 (uint32_t)e[8 * p + 4] | ((uint32_t)e[8 * p + 5] << 16),
                                 (uint32_t)e[8 * p + 6] | ((uint32_t)e[8 * p + 7] << 16));
-          *reinterpret_cast<uint4*>(my_aux + sw128_offset(r, 8 * p)) = pk;
+          if ((p >> 2) == half) *reinterpret_cast<uint4*>(my_aux + sw128_offset(r, 8 * p)) = pk;
         }
       }
       signal_a();
@@ -382,49 +409,48 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
           // conv1 (+ pool conv) of block `stage` finished: y = ReLU(Y + b1) -> activation rows; pool branch
           const BlockDesc& bd = pr.blocks[stage];
           wait_mma();
-          uint32_t acc[C];  // the whole 64-channel row: four loads in flight, one wait
+          uint32_t acc[C / 2];  // this thread's 32 channels: both loads in flight, one wait
 #pragma unroll
-          for (int c0 = 0; c0 < C; c0 += 16) tmem_ld16_nowait(tbase + TY + c0, acc + c0);
+          for (int cc = 0; cc < C / 2; cc += 16) tmem_ld16_nowait(tbase + TY + half * 32 + cc, acc + cc);
           tmem_ld_wait();
 #pragma unroll
-          for (int c0 = 0; c0 < C; c0 += 16) {
+          for (int cc = 0; cc < C / 2; cc += 16) {
+            const int c0 = half * 32 + cc;
             float y[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              y[j] = fmaxf(__uint_as_float(acc[c0 + j]) + vec[64 + stage * VEC_BLOCK + 128 + c0 + j], 0.0f);
+              y[j] = fmaxf(__uint_as_float(acc[cc + j]) + vec[64 + stage * VEC_BLOCK + 128 + c0 + j], 0.0f);
             uint4 lo, hi;
             pack16(y, lo, hi);
             if (g.real) store_row16(my_buf, GUARD + r, c0 >> 3, lo, hi);
           }
           if (bd.gpool) {
             const int G = bd.gpool;
-            for (int c0 = 0; c0 < G; c0 += 16) {
+            for (int c0 = half * 16; c0 < G; c0 += 32) {
               float p[16];
               tmem_ld16(tbase + TP + c0, p);
 #pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(my_scratch + r * MAX_G + ((((c0 + j) >> 2) ^ (r & 7)) << 2)) = make_float4(p[j], p[j + 1], p[j + 2], p[j + 3]);  // 16-byte chunks XOR-swizzled by row: conflict-free
+              for (int j = 0; j < 16; j += 4)  // 16-byte chunks XOR-swizzled by row: conflict-free
+                *reinterpret_cast<float4*>(scratch + r * MAX_G + ((((c0 + j) >> 2) ^ (r & 7)) << 2)) =
+                    make_float4(p[j], p[j + 1], p[j + 2], p[j + 3]);
             }
-            epi_barrier();
-            for (int i = tid; i < ppc * G; i += EPI_THREADS) {  // mean and max over the board, blocks.py:68-70
-              const int sl = i / G, ch = i - sl * G;
-              const int gq = sl / ppt, lq = sl - gq * ppt;
-              const float* src = scratch + gq * TILE_M * MAX_G;
+            grp_barrier(grp);
+            for (int i = q; i < ppt * G; i += GT) {  // mean and max over the board, blocks.py:68-70
+              const int lq = i / G, ch = i - lq * G;
               float s = 0.0f, m = -INFINITY;
               for (int yy = 0; yy < Hh; ++yy)
                 for (int xx = 0; xx < W; ++xx) {
                   const int rr = lq * Sp + yy * PW + xx;
-                  float x = src[rr * MAX_G + ((((ch >> 2) ^ (rr & 7)) << 2) | (ch & 3))];
+                  float x = scratch[rr * MAX_G + ((((ch >> 2) ^ (rr & 7)) << 2) | (ch & 3))];
                   s += x;
                   m = fmaxf(m, x);
                 }
-              pool_cat[sl * 2 * MAX_G + ch] = s / (float)(W * Hh);
-              pool_cat[sl * 2 * MAX_G + G + ch] = m;
+              pcat[lq * 2 * MAX_G + ch] = s / (float)(W * Hh);
+              pcat[lq * 2 * MAX_G + G + ch] = m;
             }
-            epi_barrier();
-            // pool_linear, blocks.py:72 (a_aux is free between the pool conv and the next block's input)
-            dense_small(bd.lin_wT, bd.lin_b, 2 * G, C, pool_cat, 2 * MAX_G, ppc, pool_out, C, false,
-                        reinterpret_cast<float*>(a_aux), tid);
+            grp_barrier(grp);
+            // pool_linear, blocks.py:72 (the pool rows are dead: partial sums reuse their space)
+            dense_small(bd.lin_wT, bd.lin_b, 2 * G, C, pcat, 2 * MAX_G, ppt, pout, C, false, scratch, q, grp);
           }
           signal_a();
         }
@@ -435,22 +461,23 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
         const bool last = stage + 1 == pr.n_blocks;
         const BlockDesc* nb = last ? nullptr : &pr.blocks[stage + 1];
         const float* nv = vec + 64 + (stage + 1) * VEC_BLOCK;  // the next block's pre-activation vectors
-        uint32_t xacc[C];
+        uint32_t xacc[C / 2];
 #pragma unroll
-        for (int c0 = 0; c0 < C; c0 += 16) tmem_ld16_nowait(tbase + TX + c0, xacc + c0);
+        for (int cc = 0; cc < C / 2; cc += 16) tmem_ld16_nowait(tbase + TX + half * 32 + cc, xacc + cc);
         tmem_ld_wait();
 #pragma unroll
-        for (int c0 = 0; c0 < C; c0 += 16) {
+        for (int cc = 0; cc < C / 2; cc += 16) {
+          const int c0 = half * 32 + cc;
           float x[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(xacc[c0 + j]);
+          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(xacc[cc + j]);
           if (is_stem) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j] + vec[c0 + j], 0.0f);
           }
           if (add_pool && g.real) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] += pool_out[slot * C + c0 + j];
+            for (int j = 0; j < 16; ++j) x[j] += pout[g.lp * C + c0 + j];
           }
           if ((is_stem || add_pool) && !last) tmem_st16(tbase + TX + c0, x);
           if (!last) {
@@ -471,34 +498,34 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
             // trunk finished: features at the players' cells (mask-multiply-sum, model.py:187-190)
             if (g.cell == v.p1)
 #pragma unroll
-              for (int j = 0; j < 16; ++j) catb[(slot * 2 + 0) * CAT + c0 + j] = x[j];
+              for (int j = 0; j < 16; ++j) catb[(g.lp * 2 + 0) * CAT + c0 + j] = x[j];
             if (g.cell == v.p2)
 #pragma unroll
-              for (int j = 0; j < 16; ++j) catb[(slot * 2 + 1) * CAT + c0 + j] = x[j];
+              for (int j = 0; j < 16; ++j) catb[(g.lp * 2 + 1) * CAT + c0 + j] = x[j];
           }
         }
         if (!last) signal_a();
       }
       tc_fence_before();
 
-      // ---- DeepSet heads on CUDA cores (model.py:192-213); slot sl -> position t * ppc + sl
+      // ---- DeepSet heads on CUDA cores (model.py:192-213); slot sl -> position t * ppt + sl
       const int P = pr.P, H = pr.H;
-      const int n_pos = min(ppc, n_rows - t * ppc);
-      for (int i = tid; i < n_pos * 2 * P; i += EPI_THREADS) {
+      const int n_pos = min(ppt, n_rows - t * ppt);
+      for (int i = q; i < n_pos * 2 * P; i += GT) {
         const int j = i % P, pl = (i / P) & 1, sl = i / (2 * P);
-        RowView q = row_view(rows[t * ppc + sl], games);
+        RowView q = row_view(rows[t * ppt + sl], games);
         const float side0 = (pl ? q.s2 : q.s1) / 10.0f, side1 = (float)(pl ? q.mud2 : q.mud1) / 10.0f, side2 = q.progress;
         float acc = __ldg(pr.enc_b + j) + __ldg(pr.enc_w + j * 3) * side0 + __ldg(pr.enc_w + j * 3 + 1) * side1 +
                     __ldg(pr.enc_w + j * 3 + 2) * side2;
         catb[(sl * 2 + pl) * CAT + C + j] = fmaxf(acc, 0.0f);
       }
-      for (int i = tid; i < n_pos * 2 * (MAX_P - P); i += EPI_THREADS)  // the buffer held operand bits: finite padding
+      for (int i = q; i < n_pos * 2 * (MAX_P - P); i += GT)  // the buffer held operand bits: finite padding
         catb[(i / (MAX_P - P)) * CAT + C + P + i % (MAX_P - P)] = 0.0f;
-      epi_barrier();
+      grp_barrier(grp);
       // combiner: h_i = ReLU(Linear(C + P, H)(cat(f_i, e_i)))
-      dense_small(pr.comb_wT, pr.comb_b, C + P, H, catb, CAT, n_pos * 2, hid, MAX_H, true, head_part, tid);
+      dense_small(pr.comb_wT, pr.comb_b, C + P, H, catb, CAT, n_pos * 2, hid, MAX_H, true, head_part, q, grp);
       // policy / value heads on cat(h_i, h_1 + h_2): one warp per position, lanes over the hidden units
-      for (int sl = warp; sl < n_pos; sl += EPI_THREADS / 32) {
+      for (int sl = (q >> 5); sl < n_pos; sl += GT / 32) {
         float z[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) z[i] = 0.0f;
@@ -514,7 +541,7 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
 #pragma unroll
-          for (int sh = 16; sh > 0; sh >>= 1) z[i] += __shfl_xor_sync(0xffffffffu, z[i], sh);
+          for (int sh_ = 16; sh_ > 0; sh_ >>= 1) z[i] += __shfl_xor_sync(0xffffffffu, z[i], sh_);
         }
         if (lane == 0) {
           float o[12];
@@ -537,13 +564,13 @@ cnn_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
 #pragma unroll
           for (int j = 0; j < 12; ++j) ok = ok && isfinite(o[j]);
           if (!ok) atomicCAS(error_flag, 0, (int)AR_ERR_NONFINITE);
-          float4* dst = reinterpret_cast<float4*>(out + (size_t)(t * ppc + sl) * 12);
+          float4* dst = reinterpret_cast<float4*>(out + (size_t)(t * ppt + sl) * 12);
           dst[0] = make_float4(o[0], o[1], o[2], o[3]);
           dst[1] = make_float4(o[4], o[5], o[6], o[7]);
           dst[2] = make_float4(o[8], o[9], o[10], o[11]);
         }
       }
-      epi_barrier();  // scratch is reused by the next tile
+      grp_barrier(grp);  // the buffers are reused by the next tile
     }
   }
   tc_fence_before();
@@ -740,8 +767,7 @@ struct Model : LeafEvaluator {
     pr.comb_wT = dfl + o_combw; pr.comb_b = dfl + o_combb;
     pr.head_w = dfl + o_headw; pr.head_b = dfl + o_headb;
     smem_bytes = (size_t)NG * (A_BYTES + AUX_BYTES) + N_STAGES * W_STAGE_BYTES +
-                 (size_t)NG * MAX_PPT * 2 * MAX_G * 4 + (size_t)NG * MAX_PPT * C * 4 + 256 + 1024;
-    if (const char* m = getenv("AR_CNN_DESC_MODE")) pr.desc_mode = atoi(m);
+                 (size_t)NG * MAX_PPT * 2 * MAX_G * 4 + (size_t)NG * MAX_PPT * C * 4 + 512 + 1024;
     const size_t smem_limit = (size_t)228 * 1024 / CTAS_PER_SM - 1024;  // per CTA, CTAS_PER_SM resident
     pr.vec_in_smem = smem_bytes + vecs.size() * 4 <= smem_limit ? 1 : 0;
     if (pr.vec_in_smem) smem_bytes += vecs.size() * 4;
@@ -756,8 +782,9 @@ struct Model : LeafEvaluator {
   cudaError_t forward(const EvalRow* rows, const uint32_t* n_rows_dev, int n_rows_max, const ar_game_pod* games,
                       const uint16_t* maze_tab, float* out, int* error_flag, cudaStream_t stream) const override {
     if (n_rows_max <= 0) return cudaSuccess;
-    int tiles = (n_rows_max + pr.ppt * NG - 1) / (pr.ppt * NG);
-    int grid = tiles < n_sms * CTAS_PER_SM ? tiles : n_sms * CTAS_PER_SM;
+    int tiles = (n_rows_max + pr.ppt - 1) / pr.ppt;
+    int ctas = (tiles + NG - 1) / NG;
+    int grid = ctas < n_sms * CTAS_PER_SM ? ctas : n_sms * CTAS_PER_SM;
     cnn_forward_kernel<<<grid, THREADS, smem_bytes, stream>>>(rows, n_rows_dev, n_rows_max, games, maze_tab, pr, out,
                                                               error_flag);
     return cudaGetLastError();
