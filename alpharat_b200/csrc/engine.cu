@@ -1169,11 +1169,13 @@ static void attribute_cheese(const ar_game_pod& pod, ar_game_summary& s, const a
       nxt = final_cheese; n1 = fp1; n2 = fp2;
     }
     uint64_t gone = cur & ~nxt;
-    for (int c = 0; c < cells; ++c)
-      if ((gone >> c) & 1) {
-        bool a = n1 == c, b = n2 == c;
-        s.cheese_outcomes[c] = (a && b) ? 1 : a ? 0 : b ? 3 : 2;
-      }
+    while (gone) {  // almost always empty: visit only the pieces that disappeared
+      const int c = __builtin_ctzll(gone);
+      gone &= gone - 1;
+      if (c >= cells) break;
+      bool a = n1 == c, b = n2 == c;
+      s.cheese_outcomes[c] = (a && b) ? 1 : a ? 0 : b ? 3 : 2;
+    }
   }
 }
 
@@ -1216,14 +1218,26 @@ ar_status ar_selfplay_download(ar_engine* e, ar_game_summary* summaries, ar_posi
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(e->h_dense, e->d_dense, total * sizeof(ar_position_record), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    for (int i = 0; i < n; ++i)
-      memcpy(positions + (size_t)i * positions_stride, e->h_dense + off[i],
-             (size_t)summaries[i].n_positions * sizeof(ar_position_record));
   }
   e->launches += 1;
   e->d2h += (uint64_t)n * sizeof(ar_game_summary) + total * sizeof(ar_position_record);
-  for (int i = 0; i < n; ++i)
-    attribute_cheese(e->h_games[i], summaries[i], positions + (size_t)i * positions_stride);
+  // scatter into the caller's strided array + cheese attribution, split over a few host threads
+  auto finish = [&](int lo, int hi) {
+    for (int i = lo; i < hi; ++i) {
+      ar_position_record* dst = positions + (size_t)i * positions_stride;
+      if (summaries[i].n_positions)
+        memcpy(dst, e->h_dense + off[i], (size_t)summaries[i].n_positions * sizeof(ar_position_record));
+      attribute_cheese(e->h_games[i], summaries[i], dst);
+    }
+  };
+  const int n_thr = n >= 4096 ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+  if (n_thr <= 1) {
+    finish(0, n);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_thr; ++t) pool.emplace_back(finish, (int)((int64_t)n * t / n_thr), (int)((int64_t)n * (t + 1) / n_thr));
+    for (auto& th : pool) th.join();
+  }
   return AR_OK;
 }
 
