@@ -136,7 +136,7 @@ EXPORTED_SYMBOLS = (
     "ar_engine_create", "ar_engine_destroy", "ar_last_error", "ar_abi_version",
     "ar_engine_load_weights", "ar_search_batch", "ar_selfplay_run", "ar_selfplay_upload",
     "ar_selfplay_run_resident", "ar_selfplay_download", "ar_encode_observations",
-    "ar_nn_forward",
+    "ar_nn_forward", "ar_engine_set_eval_cache",
 )
 
 _LIB = None
@@ -187,6 +187,8 @@ def load_library() -> C.CDLL:
     lib.ar_encode_observations.restype = C.c_int
     lib.ar_nn_forward.argtypes = [eng, P(GamePod), C.c_int32, P(C.c_float), P(C.c_float), P(C.c_float), P(C.c_float)]
     lib.ar_nn_forward.restype = C.c_int
+    lib.ar_engine_set_eval_cache.argtypes = [eng, C.c_uint32]
+    lib.ar_engine_set_eval_cache.restype = C.c_int
     if lib.ar_abi_version() != AR_ABI_VERSION:
         raise RuntimeError(f"ABI mismatch: library {lib.ar_abi_version()} != python {AR_ABI_VERSION}")
     _LIB = lib

@@ -312,6 +312,30 @@ struct SlotState {
   uint32_t pad[1];
 };
 
+// Evaluation cache (CachedBackend / NNCache, crates/alpharat-sampling/src/cached_backend.rs:54-120,
+// nn_cache.rs): one direct-mapped table per resident tree, the GPU counterpart of the reference's
+// thread-local caches.  A leaf whose position was already scored skips the evaluator; the search cannot
+// tell (it still counts as an nn_eval), so results are bit-identical with and without the cache.  The key
+// is the whole position (not only a hash), tagged with the game index and the turn.
+struct __align__(16) CacheEnt {
+  uint64_t cheese;
+  uint32_t pos, score;      // GPack
+  uint32_t game_idx;
+  uint32_t turn_tag;        // turn | 0x80000000 (0 = empty)
+  uint32_t pad[2];
+  float out[12];
+};
+static_assert(sizeof(CacheEnt) == 80, "CacheEnt layout");
+__device__ __forceinline__ uint32_t cache_index(const GPack& g, uint32_t game, uint32_t turn_tag, uint32_t mask) {
+  uint64_t h = g.cheese * 0x9E3779B97F4A7C15ull;
+  h ^= (((uint64_t)g.pos << 32) | g.score) * 0xC2B2AE3D27D4EB4Full;
+  h ^= (((uint64_t)game << 20) ^ turn_tag) * 0x165667B19E3779F9ull;
+  h ^= h >> 29;
+  h *= 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 32;
+  return (uint32_t)h & mask;
+}
+
 struct NnParams {
   SlotState* slots;
   TpEntry* tp_store;        // [n_slots][batch_cap]
@@ -320,6 +344,9 @@ struct NnParams {
   const float* nn_out;      // [rows][12] from the previous step
   uint32_t* done_slots;
   uint32_t max_rows;
+  CacheEnt* cache;          // [n_slots][cache_mask + 1] or null
+  GPack* key_store;         // [n_slots][batch_cap]: positions of the leaves waiting for their evaluation
+  uint32_t cache_mask;
 };
 
 __global__ void nn_init_slots_kernel(SlotState* slots, int n) {
@@ -370,6 +397,67 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
   }
   TpEntry* tp_g = q.tp_store + (size_t)slot * p.batch_cap;
 
+  CacheEnt* const cbase = q.cache ? q.cache + (size_t)slot * (q.cache_mask + 1) : nullptr;
+  GPack* const keys_g = q.key_store + (size_t)slot * p.batch_cap;
+  // populate + backup in to_process order (search.rs:1028-1058); the batch entries are in cx.tp().
+  // kind 0: scored by the evaluator in the previous step, 1: terminal, 2: evaluation-cache hit.
+  auto process_batch = [&](int n_tp) {
+    uint32_t row = st.row_base, nn_b = 0, term_b = 0;
+    for (int e = 0; e < n_tp; ++e) {
+      const TpEntry te = cx.tp()[e];
+      if (te.kind == 1) {
+        term_b += 1;
+        backup_entry(cx, e, 0.0f, 0.0f, nullptr, nullptr, lane);
+        continue;
+      }
+      const float* o = te.kind == 0 ? q.nn_out + (size_t)row * 12 : cbase[te.pad].out;
+#ifdef AR_CACHE_VERIFY
+      if (te.kind == 0 && te.pad != 0 && lane < 12) {
+        const float cv = cbase[te.pad - 1].out[lane];
+        if (cv != o[lane]) {
+          atomicAdd(&p.counters[5], 1ull);
+          if (lane == 10) printf("slot %d gi %d turn %d depth %d idx %d cached v %g fresh v %g\n", slot, st.gi, turn, te.depth, te.pad - 1, cv, o[lane]);
+        } else atomicAdd(&p.counters[4], 1ull);
+      }
+#endif
+      row += te.kind == 0 ? 1u : 0u;
+      nn_b += 1;
+      if (te.node == 0 && sp.noise_epsilon > 0.0f) {
+        // populate first, then noise, then backup (search.rs:1034-1052)
+        backup_entry(cx, e, o[10], o[11], o, o + 5, lane, /*populate_only=*/true);
+        apply_root_noise(cx, sp, rng, lane);
+        backup_entry(cx, e, o[10], o[11], nullptr, nullptr, lane);
+      } else {
+        backup_entry(cx, e, o[10], o[11], o, o + 5, lane);
+      }
+    }
+    if (cbase) {  // remember what the evaluator returned (after every hit of this batch has been read)
+      uint32_t rows_before = 0;
+      for (int e0 = 0; e0 < n_tp; e0 += 32) {
+        const int e = e0 + lane;
+        const bool fresh = e < n_tp && cx.tp()[e].kind == 0;
+        const uint32_t fm = __ballot_sync(FULL, fresh);
+        if (fresh) {
+          const uint32_t r = st.row_base + rows_before + __popc(fm & ((1u << lane) - 1u));
+          const GPack gp = keys_g[e];
+          const uint32_t tt = (uint32_t)(turn + cx.tp()[e].depth) | 0x80000000u;
+          CacheEnt* ce = cbase + cache_index(gp, (uint32_t)st.gi, tt, q.cache_mask);
+          const float4* src = reinterpret_cast<const float4*>(q.nn_out + (size_t)r * 12);
+          *reinterpret_cast<uint4*>(ce) = make_uint4((uint32_t)gp.cheese, (uint32_t)(gp.cheese >> 32), gp.pos, gp.score);
+          *reinterpret_cast<uint4*>(&ce->game_idx) = make_uint4((uint32_t)st.gi, tt, 0u, 0u);
+          float4* dst = reinterpret_cast<float4*>(ce->out);
+          dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+        }
+        rows_before += __popc(fm);
+      }
+    }
+    st.nn += nn_b;
+    st.term += term_b;
+    uint32_t produced = nn_b + term_b;
+    produced = produced > 1u ? produced : 1u;
+    st.remaining = st.remaining > produced ? st.remaining - produced : 0u;
+  };
+
   bool moved = false;
   for (int iter = 0; iter < 3 && cx.error == 0; ++iter) {
     if (st.phase == PH_IDLE) {
@@ -402,34 +490,10 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
       if (budget < COMPACT_ITERS_PER_STEP / 2) break;  // gather in the next step
     }
     if (st.phase == PH_WAIT_EVAL) {
-      // ---- populate + backup in to_process order (search.rs:1028-1058)
       const int n_tp = (int)st.n_tp;
       for (int e = lane; e < n_tp; e += 32) cx.tp()[e] = tp_g[e];
       __syncwarp();
-      uint32_t row = st.row_base, nn_b = 0, term_b = 0;
-      for (int e = 0; e < n_tp; ++e) {
-        if (cx.tp()[e].kind == 0) {
-          const float* o = q.nn_out + (size_t)row * 12;
-          row += 1;
-          nn_b += 1;
-          if (cx.tp()[e].node == 0 && sp.noise_epsilon > 0.0f) {
-            // populate first, then noise, then backup (search.rs:1034-1052)
-            backup_entry(cx, e, o[10], o[11], o, o + 5, lane, /*populate_only=*/true);
-            apply_root_noise(cx, sp, rng, lane);
-            backup_entry(cx, e, o[10], o[11], nullptr, nullptr, lane);
-          } else {
-            backup_entry(cx, e, o[10], o[11], o, o + 5, lane);
-          }
-        } else {
-          term_b += 1;
-          backup_entry(cx, e, 0.0f, 0.0f, nullptr, nullptr, lane);
-        }
-      }
-      st.nn += nn_b;
-      st.term += term_b;
-      uint32_t produced = nn_b + term_b;
-      produced = produced > 1u ? produced : 1u;
-      st.remaining = st.remaining > produced ? st.remaining - produced : 0u;
+      process_batch(n_tp);
       st.phase = PH_GATHER;
     }
     if (st.phase == PH_GATHER) {
@@ -528,16 +592,52 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
       }
       if (cx.error) break;
       __syncwarp();
+      uint32_t n_hit = 0;
+      if (cbase) {  // evaluation-cache lookup: hits become kind 2 and never reach the queue
+        for (int e0 = 0; e0 < n_tp; e0 += 32) {
+          const int e = e0 + lane;
+          bool hit = false;
+          if (e < n_tp) {
+            TpEntry te = cx.tp()[e];
+            if (te.kind == 0) {
+              const GPack gp = cx.tp_state()[e];
+              const uint32_t tt = (uint32_t)(turn + te.depth) | 0x80000000u;
+              const uint32_t idx = cache_index(gp, (uint32_t)st.gi, tt, q.cache_mask);
+              const uint4 k0 = *reinterpret_cast<const uint4*>(cbase + idx);
+              const uint2 k1 = *reinterpret_cast<const uint2*>(&cbase[idx].game_idx);
+              hit = k0.x == (uint32_t)gp.cheese && k0.y == (uint32_t)(gp.cheese >> 32) && k0.z == gp.pos &&
+                    k0.w == gp.score && k1.x == (uint32_t)st.gi && k1.y == tt;
+              if (hit) {
+#ifdef AR_CACHE_VERIFY
+                te.pad = (uint16_t)(idx + 1);
+                cx.tp()[e] = te;
+                keys_g[e] = gp;
+                hit = false;
+#else
+                te.kind = 2;
+                te.pad = (uint16_t)idx;
+                cx.tp()[e] = te;
+#endif
+              } else {
+                keys_g[e] = gp;
+              }
+            }
+          }
+          n_hit += __popc(__ballot_sync(FULL, hit));
+        }
+        __syncwarp();
+      }
       uint32_t evmask = __ballot_sync(FULL, lane < n_tp && cx.tp()[lane].kind == 0);
       uint32_t evmask_hi = n_tp > 32 ? __ballot_sync(FULL, lane + 32 < n_tp && cx.tp()[lane + 32].kind == 0) : 0u;
       const uint32_t n_eval = __popc(evmask) + __popc(evmask_hi);
       st.n_tp = (uint32_t)n_tp;
+      if (cbase && lane == 0 && (n_hit | n_eval)) {
+        atomicAdd(&p.counters[6], (unsigned long long)n_hit);
+        atomicAdd(&p.counters[7], (unsigned long long)n_eval);
+      }
       if (n_eval == 0) {
-        // nothing to evaluate (terminal-only batch): back up at once and keep going
-        for (int e = 0; e < n_tp; ++e) backup_entry(cx, e, 0.0f, 0.0f, nullptr, nullptr, lane);
-        st.term += (uint32_t)n_tp;
-        uint32_t produced = n_tp > 1 ? (uint32_t)n_tp : 1u;
-        st.remaining = st.remaining > produced ? st.remaining - produced : 0u;
+        // nothing to evaluate (terminals and cache hits only): back up at once and keep going
+        process_batch(n_tp);
         continue;
       }
       uint32_t rb = 0;
@@ -660,6 +760,10 @@ struct ar_engine {
   float* d_queue_out = nullptr;
   uint32_t* d_n_rows = nullptr;   // [0] queue length, [1] done slots
   uint64_t nn_steps = 0;
+  // evaluation cache (ar_engine_set_eval_cache)
+  CacheEnt* d_cache = nullptr;
+  GPack* d_key_store = nullptr;
+  uint32_t cache_entries = 0;     // per resident tree, power of two (0 = disabled)
 };
 
 static thread_local std::string g_create_error;
@@ -869,6 +973,7 @@ void ar_engine_destroy(ar_engine* e) {
   cudaFree(e->d_dense); cudaFree(e->d_offsets); cudaFree(e->d_maze_tab);
   if (e->h_dense) cudaFreeHost(e->h_dense);
   cudaFree(e->d_slots); cudaFree(e->d_tp_store); cudaFree(e->d_queue); cudaFree(e->d_queue_out); cudaFree(e->d_n_rows);
+  cudaFree(e->d_cache); cudaFree(e->d_key_store);
   delete e->eval;
   if (e->h_progress) cudaFreeHost(e->h_progress);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -899,6 +1004,24 @@ ar_status ar_engine_load_weights(ar_engine* e, int32_t arch, int32_t width, int3
   e->arch = arch;
   e->nn_width = width;
   e->nn_height = height;
+  return AR_OK;
+}
+
+// CachedBackend::new(inner, capacity) (cached_backend.rs:62-70): `entries_per_tree` positions per resident
+// tree, rounded up to a power of two and capped at 65536 and at 8 GiB in total; 0 disables the cache.
+ar_status ar_engine_set_eval_cache(ar_engine* e, uint32_t entries_per_tree) {
+  if (!e) return AR_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  cudaFree(e->d_cache);
+  e->d_cache = nullptr;
+  e->cache_entries = 0;
+  if (entries_per_tree == 0) return AR_OK;
+  uint32_t n = 1;
+  while (n < entries_per_tree && n < 65536u) n <<= 1;
+  while (n > 64 && (size_t)n * e->n_slots * sizeof(CacheEnt) > ((size_t)8 << 30)) n >>= 1;
+  CK(cudaMalloc(&e->d_cache, (size_t)n * e->n_slots * sizeof(CacheEnt)));
+  e->cache_entries = n;
   return AR_OK;
 }
 
@@ -947,6 +1070,7 @@ static ar_status ensure_nn_buffers(ar_engine* e) {
   CK(cudaMalloc(&e->d_queue, max_rows * sizeof(EvalRow)));
   CK(cudaMalloc(&e->d_queue_out, max_rows * 12 * sizeof(float)));
   CK(cudaMalloc(&e->d_n_rows, 2 * sizeof(uint32_t)));
+  CK(cudaMalloc(&e->d_key_store, max_rows * sizeof(GPack)));
   return AR_OK;
 }
 
@@ -981,6 +1105,13 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
     q.nn_out = e->d_queue_out;
     q.done_slots = e->d_n_rows + 1;
     q.max_rows = (uint32_t)((size_t)slots * e->batch_cap);
+    q.key_store = e->d_key_store;
+    if (e->cache_entries) {
+      // a run starts with an empty cache: game indices and weights may have changed since the last one
+      q.cache = e->d_cache;
+      q.cache_mask = e->cache_entries - 1;
+      CK(cudaMemsetAsync(e->d_cache, 0, (size_t)slots * e->cache_entries * sizeof(CacheEnt), e->stream));
+    }
     CK(cudaMemsetAsync(e->d_n_rows, 0, 2 * sizeof(uint32_t), e->stream));
     nn_init_slots_kernel<<<(slots + 127) / 128, 128, 0, e->stream>>>(e->d_slots, slots);
     CK(cudaGetLastError());
@@ -1134,6 +1265,8 @@ static ar_status run_resident(ar_engine* e, const ar_search_cfg* cfg, ar_progres
     stats->path_nodes = c[0];
     stats->new_nodes = c[1];
     stats->kernel_launches = e->launches;
+    stats->cache_hits = c[6];
+    stats->cache_misses = c[7];
 #ifdef AR_PHASE_TIMING
     fprintf(stderr, "[phase cycles] gather=%llu backup=%llu advance=%llu total=%llu\n", c[2], c[3], c[4], c[5]);
 #endif

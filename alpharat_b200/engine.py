@@ -85,6 +85,11 @@ class Engine:
                     "ar_engine_load_weights")
         self.has_evaluator = arch != N.AR_ARCH_UNIFORM
 
+    def set_eval_cache(self, entries_per_tree: int) -> None:
+        """Evaluation cache of the NN-guided mode (`cache_size` of rust_self_play; CachedBackend,
+        cached_backend.rs:54-120): positions per resident tree, 0 disables."""
+        self._check(self._lib.ar_engine_set_eval_cache(self._h, int(entries_per_tree)), "ar_engine_set_eval_cache")
+
     # --- search ----------------------------------------------------------------------------
     def search_batch(self, pods, cfg: N.SearchCfg, seeds: Sequence[int]):
         n = len(pods)

@@ -165,6 +165,8 @@ def cuda_self_play(
             from .weights import load_checkpoint_into
 
             load_checkpoint_into(engine, checkpoint)
+        if engine.has_evaluator:
+            engine.set_eval_cache(cache_size)  # per resident tree (the reference: per worker thread)
         t0 = time.perf_counter()
         pods = pods_array(specs)
         summaries, pos, stride, st = engine.selfplay(pods, cfg, seeds,
@@ -178,11 +180,6 @@ def cuda_self_play(
                 raise IOError(str(e)) from e
         st.elapsed_secs = time.perf_counter() - t0
         stats = SelfPlayStats(st)
-        if cache_size and engine.has_evaluator:
-            # CachedBackend (cached_backend.rs:54-120) only skips repeated evaluations of a
-            # deterministic evaluator, so results do not depend on it.  On the GPU every leaf is
-            # evaluated (the evaluator is ~10 % of a step): all lookups are reported as misses.
-            stats.cache_hits, stats.cache_misses = 0, stats.total_nn_evals
         if return_records:
             return stats, summaries, pos, stride
         return stats

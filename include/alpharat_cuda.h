@@ -14,6 +14,8 @@
  *                                              crates/alpharat-sampling/src/flat_encoder.rs:52-124
  *   ar_nn_forward     <- Backend::evaluate_batch (ONNX / TensorRT)
  *                                              crates/alpharat-sampling/src/backends/onnx.rs:176-245
+ *   ar_engine_set_eval_cache <- CachedBackend::new (rust_self_play's cache_size)
+ *                                              crates/alpharat-sampling/src/cached_backend.rs:54-120
  *
  * Plain C types only: pointers and sizes, caller-owned host buffers, fixed-layout
  * little-endian PODs.  The engine owns all device memory.  An engine handle is
@@ -178,6 +180,12 @@ uint32_t ar_abi_version(void);
  * state_dict in f32; the engine folds eval-mode BatchNorm, converts and uploads. */
 ar_status ar_engine_load_weights(ar_engine* e, int32_t arch, int32_t width, int32_t height,
                                  const ar_tensor_desc* tensors, int32_t n_tensors);
+
+/* Evaluation cache of the NN-guided mode: entries_per_tree positions per resident tree (rounded up to a
+ * power of two, at most 65536; 0 disables).  Replaces the thread-local NNCache behind CachedBackend: a leaf
+ * whose exact position was scored before skips the evaluator; search results do not depend on it.
+ * ar_stats.cache_hits / cache_misses report the lookups of a run. */
+ar_status ar_engine_set_eval_cache(ar_engine* e, uint32_t entries_per_tree);
 
 /* n independent fresh-tree searches (rust_mcts_search semantics, one RNG per search
  * seeded with SmallRng::seed_from_u64(seeds[i])). */

@@ -135,3 +135,42 @@ def test_nn_search_within_tolerance_of_fp32_reference(oracle):
           f"value rel err: median {np.median(verr):.4f} p90 {np.percentile(verr, 90):.4f} max {np.max(verr):.4f}")
     assert np.median(l1) <= L1_MEDIAN_TOL and np.percentile(l1, 90) <= L1_P90_TOL, l1
     assert np.median(verr) <= V_MEDIAN_TOL and np.percentile(verr, 90) <= V_P90_TOL, verr
+
+
+@pytest.mark.parametrize("arch,make_sd,noise", [
+    (N.AR_ARCH_MLP, lambda: make_mlp_state_dict(1, 349), 0.0),
+    (N.AR_ARCH_MLP, lambda: make_mlp_state_dict(1, 349), 0.25),
+    (N.AR_ARCH_CNN, lambda: make_cnn_state_dict(3, ("res", "res", "gpool")), 0.0),
+])
+def test_eval_cache_changes_nothing_but_the_evaluator_load(oracle, arch, make_sd, noise):
+    """`cache_size` (CachedBackend, cached_backend.rs:54-120): with the evaluation cache on, every record is
+    bit-identical to the run without it (and to the oracle), lookups add up to the evaluations the search
+    counted, and transpositions do hit.  A tiny cache (constant evictions) must be just as exact."""
+    n = 6
+    specs = make_games(n, width=7, height=7, cheese_count=10, max_turns=24, first_index=300)
+    pods = pods_array(specs)
+    cfg = search_cfg(simulations=200, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103,
+                     noise_epsilon=noise)
+    seeds = [40 + i for i in range(n)]
+    with Engine(concurrent_games=4, max_turns=24, max_batch_size=16, max_simulations=200, pool_nodes=8192) as eng:
+        eng.load_weights(arch, 7, 7, make_sd())
+        plain = eng.selfplay(pods, cfg, seeds)
+        assert plain[3].cache_hits == 0 and plain[3].cache_misses == 0
+        eng.set_eval_cache(4096)
+        cached = eng.selfplay(pods, cfg, seeds)
+        again = eng.selfplay(pods, cfg, seeds)  # every run starts from an empty cache
+        eng.set_eval_cache(16)
+        tiny = eng.selfplay(pods, cfg, seeds)
+        eng.set_eval_cache(0)
+        off = eng.selfplay(pods, cfg, seeds)
+        cpu = oracle_selfplay(oracle, pods, cfg, seeds, n_threads=1, eval_cb=gpu_eval_callback(eng))
+    compare_selfplay(cached, cpu, n)
+    compare_selfplay(tiny, cpu, n)
+    compare_selfplay(plain, cpu, n)
+    compare_selfplay(off, cpu, n)
+    for run in (cached, again, tiny):
+        st = run[3]
+        assert st.cache_hits + st.cache_misses == st.total_nn_evals == plain[3].total_nn_evals
+    assert cached[3].cache_hits > 0 and cached[3].cache_hits == again[3].cache_hits
+    assert tiny[3].cache_hits <= cached[3].cache_hits
+    assert off[3].cache_hits == 0 and off[3].cache_misses == 0
