@@ -292,7 +292,7 @@ def run_cuda(args) -> None:
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": algo_bytes / max(launches, 1),
-                         "note": "tree kernel is instruction-issue bound (66 % of issue slots, DRAM < 2 % of peak); "
+                         "note": "tree kernel is instruction-issue bound (68 % of issue slots, DRAM < 2 % of peak); "
                                  "traffic = DRAM/algorithmic ratio of the ncu capture x this run's algorithmic bytes; "
                                  "see profiles/r1_summary.md"},
             "cpu_baseline": base,
