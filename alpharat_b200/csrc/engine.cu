@@ -115,13 +115,23 @@ __device__ __forceinline__ void load_game(const ar_game_pod* pod, WarpCtx& cx, G
     reinterpret_cast<uint32_t*>(cx.maze())[i] =
         (i < cx.cells) ? reinterpret_cast<const uint32_t*>(pod->move_cost)[i] : 0u;
   uint16_t* tbl = const_cast<uint16_t*>(cx.steptbl());
-  for (int i = lane; i < 64 * 8; i += 32) {  // move table: target cell | mud cost << 8
-    const int c = i >> 3, a = i & 7;
-    uint32_t e = (uint32_t)c;
-    if (a < 4 && c < cx.cells) {
-      const int cost = pod->move_cost[c * 4 + a];
-      const int mag = (a & 1) ? 1 : cx.w;
-      if (cost) e = (uint32_t)(c + ((a & 2) ? -mag : mag)) | ((uint32_t)(cost >= 2 ? cost : 0) << 8);
+  for (int i = lane; i < 64 * 8; i += 32) {  // move table by OUTCOME index: target cell | mud cost << 8
+    const int c = i >> 3, oi = i & 7;
+    uint32_t e = (uint32_t)c;  // STAY, and every slot past the cell's outcomes
+    if (c < cx.cells) {
+      // outcomes are the open directions in ascending action order, then STAY (compute_outcomes, node.rs:251-283)
+      int a = -1, seen = 0;
+#pragma unroll
+      for (int d = 0; d < 4; ++d)
+        if (pod->move_cost[c * 4 + d] != 0) {
+          if (seen == oi) a = d;
+          seen += 1;
+        }
+      if (a >= 0) {
+        const int cost = pod->move_cost[c * 4 + a];
+        const int mag = (a & 1) ? 1 : cx.w;
+        e = (uint32_t)(c + ((a & 2) ? -mag : mag)) | ((uint32_t)(cost >= 2 ? cost : 0) << 8);
+      }
     }
     tbl[i] = (uint16_t)e;
   }
@@ -232,7 +242,7 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(Ru
       uint32_t rmeta = cx.pool[0].s[LANE_LINKS].y;
       int i = action_to_idx(meta_m1(rmeta), a1), j = action_to_idx(meta_m2(rmeta), a2);
       uint32_t child = reinterpret_cast<const uint32_t*>(&cx.pool[0].s[LANE_CHILD])[i * 5 + j];
-      game_step(g, a1, a2, cx.steptbl());
+      game_step(g, i, j, cx.steptbl());  // the table is indexed by outcome (blocked move = STAY's outcome)
       turn += 1;
       __syncwarp();
       AR_T0();
@@ -533,7 +543,7 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
           uint32_t rmeta = cx.pool[0].s[LANE_LINKS].y;
           int i = action_to_idx(meta_m1(rmeta), a1), j = action_to_idx(meta_m2(rmeta), a2);
           uint32_t child = reinterpret_cast<const uint32_t*>(&cx.pool[0].s[LANE_CHILD])[i * 5 + j];
-          game_step(g, a1, a2, cx.steptbl());
+          game_step(g, i, j, cx.steptbl());  // indexed by outcome
           turn += 1;
           __syncwarp();
           moved = true;
