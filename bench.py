@@ -6,8 +6,10 @@
 Workload (BASELINE.json configs[1]): PyRat 7x7 open maze, 10 cheese, 50 turns, `7x7_rust_tuned`
 (1897 sims, c_puct 0.512, fpu 0.459, force_k 0.103, batch 16), uniform priors, Dirichlet noise 0,
 4096 concurrent game trees per GPU.  One step = one pass of the hot path over one batch of
-synthetic games (`--games-per-step` per GPU, default 65536, played to completion through the
-4096 resident trees; fresh games every step).
+synthetic games (`--games-per-step` per GPU, default 131072, played to completion through the
+4096 resident trees; fresh games every step).  A step ends with a tail in which the last, longest games
+run alone (games last 12.5 turns on average, up to 50), so throughput grows with the batch: 3.25 / 3.93 /
+4.54 / 4.80 x 10^8 simulations/s at 16k / 32k / 64k / 128k games per step (profiles/r1_summary.md).
 
 Metric: self-play MCTS simulations/sec, counted as S_new = descents performed
 (nn_evals + terminals); games/hour and the reference's own S_ref (sum of root visits,
@@ -310,7 +312,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--games-per-step", type=int, default=65536)
+    ap.add_argument("--games-per-step", type=int, default=131072)
     ap.add_argument("--concurrent", type=int, default=4096)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
