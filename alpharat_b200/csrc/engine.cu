@@ -358,6 +358,7 @@ struct NnParams {
   GPack* key_store;         // [n_slots][batch_cap]: positions of the leaves waiting for their evaluation
   uint32_t cache_mask;
   int max_iters;            // gather / backup rounds a slot may chain inside one step
+  uint4* board_store;       // [n_slots][SM_TP / 16]: move table + maze of the slot's game, built once per game
 };
 
 __global__ void nn_init_slots_kernel(SlotState* slots, int n) {
@@ -401,10 +402,16 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
   GState g = g_unpack(st.g);
   Rng rng = st.rng;
   int turn = st.turn;
+  uint4* const board_g = q.board_store + (size_t)slot * (SM_TP / 16);
   if (st.gi >= 0) {
-    int dummy_turn;
-    GState dummy;
-    load_game(p.games + st.gi, cx, dummy, dummy_turn, lane);  // maze + board constants
+    // the game's move table + maze (SM_TP bytes at the start of the warp's shared memory) were built when the
+    // game was loaded: copy them back instead of rebuilding them every step
+    const ar_game_pod* pod = p.games + st.gi;
+    cx.w = pod->width;
+    cx.cells = (int)pod->width * pod->height;
+    cx.max_turns = pod->max_turns;
+    for (int i = lane; i < SM_TP / 16; i += 32) reinterpret_cast<uint4*>(cx.sm)[i] = board_g[i];
+    __syncwarp();
   }
   TpEntry* tp_g = q.tp_store + (size_t)slot * p.batch_cap;
 
@@ -483,6 +490,7 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
       }
       st.gi = (int)gi;
       load_game(p.games + gi, cx, g, turn, lane);
+      for (int i = lane; i < SM_TP / 16; i += 32) board_g[i] = reinterpret_cast<const uint4*>(cx.sm)[i];
       rng = rng_seed(p.seeds[gi]);
       st.cheese_available = __popcll(g.cheese);
       cx.epoch += 1;
@@ -774,6 +782,7 @@ struct ar_engine {
   // evaluation cache (ar_engine_set_eval_cache)
   CacheEnt* d_cache = nullptr;
   GPack* d_key_store = nullptr;
+  uint4* d_board_store = nullptr; // per-slot move table + maze image
   uint32_t cache_entries = 0;     // per resident tree, power of two (0 = disabled)
 };
 
@@ -984,7 +993,7 @@ void ar_engine_destroy(ar_engine* e) {
   cudaFree(e->d_dense); cudaFree(e->d_offsets); cudaFree(e->d_maze_tab);
   if (e->h_dense) cudaFreeHost(e->h_dense);
   cudaFree(e->d_slots); cudaFree(e->d_tp_store); cudaFree(e->d_queue); cudaFree(e->d_queue_out); cudaFree(e->d_n_rows);
-  cudaFree(e->d_cache); cudaFree(e->d_key_store);
+  cudaFree(e->d_cache); cudaFree(e->d_key_store); cudaFree(e->d_board_store);
   delete e->eval;
   if (e->h_progress) cudaFreeHost(e->h_progress);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -1082,6 +1091,7 @@ static ar_status ensure_nn_buffers(ar_engine* e) {
   CK(cudaMalloc(&e->d_queue_out, max_rows * 12 * sizeof(float)));
   CK(cudaMalloc(&e->d_n_rows, 2 * sizeof(uint32_t)));
   CK(cudaMalloc(&e->d_key_store, max_rows * sizeof(GPack)));
+  CK(cudaMalloc(&e->d_board_store, (size_t)e->n_slots * SM_TP));
   return AR_OK;
 }
 
@@ -1117,6 +1127,7 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
     q.done_slots = e->d_n_rows + 1;
     q.max_rows = (uint32_t)((size_t)slots * e->batch_cap);
     q.key_store = e->d_key_store;
+    q.board_store = e->d_board_store;
     // With the evaluation cache most batches complete without the evaluator; chaining them inside a step
     // only lengthens the step's critical path (measured: CNN config 9.1 s with 1 round, 9.7 s with 3, 16.6 s with 12).
     q.max_iters = e->cache_entries ? 1 : 3;
