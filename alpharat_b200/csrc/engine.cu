@@ -1141,25 +1141,54 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
     nn_init_slots_kernel<<<(slots + 127) / 128, 128, 0, e->stream>>>(e->d_slots, slots);
     CK(cudaGetLastError());
     e->launches += 1;
+    // 32 steps (queue reset, tree step, evaluator) are captured once into a CUDA graph and replayed: the step
+    // kernels are short (0.3-1 ms) and depend on each other, so launch gaps would otherwise show.  The host
+    // reads one counter per replay to know when every game is finished.
     const int check_every = 32;
-    for (;;) {
-      for (int it = 0; it < check_every; ++it) {
-        CK(cudaMemsetAsync(e->d_n_rows, 0, sizeof(uint32_t), e->stream));
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    cudaError_t cap = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+    if (cap == cudaSuccess) {
+      cudaError_t in_cap = cudaSuccess;
+      for (int it = 0; it < check_every && in_cap == cudaSuccess; ++it) {
+        in_cap = cudaMemsetAsync(e->d_n_rows, 0, sizeof(uint32_t), e->stream);
+        if (in_cap != cudaSuccess) break;
         nn_step_kernel<<<blocks, 128, smem, e->stream>>>(p, q);
-        CK(cudaGetLastError());
-        CK(e->eval->forward(e->d_queue, e->d_n_rows, (int)q.max_rows, p.games, e->d_maze_tab, e->d_queue_out, e->d_error,
-                            e->stream));
-        e->launches += 2;
-        e->nn_steps += 1;
+        in_cap = cudaGetLastError();
+        if (in_cap != cudaSuccess) break;
+        in_cap = e->eval->forward(e->d_queue, e->d_n_rows, (int)q.max_rows, p.games, e->d_maze_tab, e->d_queue_out,
+                                  e->d_error, e->stream);
       }
+      cap = cudaStreamEndCapture(e->stream, &graph);
+      if (in_cap != cudaSuccess) cap = in_cap;
+      if (cap == cudaSuccess) cap = cudaGraphInstantiate(&gexec, graph, 0);
+    }
+    if (cap != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      e->err = std::string("CUDA graph capture of the NN step failed: ") + cudaGetErrorString(cap);
+      return AR_ERR_CUDA;
+    }
+    ar_status loop_status = AR_OK;
+    for (;;) {
+      cudaError_t le = cudaGraphLaunch(gexec, e->stream);
+      e->launches += 2 * check_every;
+      e->nn_steps += check_every;
       uint32_t h[2] = {0, 0};
       int herr = 0;
-      CK(cudaMemcpyAsync(h, e->d_n_rows, sizeof(h), cudaMemcpyDeviceToHost, e->stream));
-      CK(cudaMemcpyAsync(&herr, e->d_error, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-      CK(cudaStreamSynchronize(e->stream));
+      if (le == cudaSuccess) le = cudaMemcpyAsync(h, e->d_n_rows, sizeof(h), cudaMemcpyDeviceToHost, e->stream);
+      if (le == cudaSuccess) le = cudaMemcpyAsync(&herr, e->d_error, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+      if (le == cudaSuccess) le = cudaStreamSynchronize(e->stream);
+      if (le != cudaSuccess) {
+        e->err = std::string("NN step: ") + cudaGetErrorString(le);
+        loop_status = AR_ERR_CUDA;
+        break;
+      }
       if (user_progress) memcpy((void*)user_progress, (const void*)e->h_progress, sizeof(ar_progress));
       if (herr != 0 || (int)h[1] >= slots) break;
     }
+    cudaGraphExecDestroy(gexec);
+    cudaGraphDestroy(graph);
+    if (loop_status != AR_OK) return loop_status;
   }
   CK(cudaEventRecord(e->ev1, e->stream));
   if (user_progress && !nn) {
