@@ -61,7 +61,9 @@ constexpr int TILE_M = 128;
 constexpr int A_BLOCK_BYTES = TILE_M * KB * 2;  // 16 KB
 constexpr int W_STAGE_BYTES = 256 * KB * 2;     // 32 KB
 constexpr int N_STAGES = 3;
-constexpr int MLP_THREADS = 192;
+constexpr int EPI_WARPS = 8;                    // two threads per tile row, 128 output columns each
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int MLP_THREADS = EPI_THREADS + 64;   // + TMA warp + MMA warp
 
 struct MlpSmem {
   uint64_t w_full[N_STAGES];
@@ -71,8 +73,20 @@ struct MlpSmem {
   uint32_t tmem_base;
 };
 
-// One CTA = 128 rows per tile.  warps 0-3: encode + epilogue (thread t owns row t and TMEM lane
-// t), warp 4: TMA weight producer, warp 5: MMA issuer (and TMEM allocation).
+// 16 TMEM columns without waiting: several loads are in flight before one wait
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t r[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+
+// One CTA = 128 rows per tile.  warps 0-7: encode + epilogue (threads r and r + 128 own row r = TMEM lane r,
+// 128 of the 256 hidden columns each), warp 8: TMA weight producer, warp 9: MMA issuer (stays converged so that
+// the descriptors live in uniform registers; tcgen05 instructions predicated on lane 0) and TMEM allocation.
 __global__ void __launch_bounds__(MLP_THREADS, 1)
 mlp_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict__ n_rows_ptr, int n_rows_arg,
                    const ar_game_pod* __restrict__ games, const uint16_t* __restrict__ maze_tab, MlpWeights w,
@@ -93,11 +107,11 @@ mlp_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
       mbar_init(&sh->w_full[s], 1);
       mbar_init(&sh->w_empty[s], 1);
     }
-    mbar_init(&sh->a_ready, 128);
+    mbar_init(&sh->a_ready, EPI_WARPS);
     mbar_init(&sh->mma_done, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(&sh->tmem_base, 256);
+  if (warp == EPI_WARPS + 1) tmem_alloc(&sh->tmem_base, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -107,7 +121,7 @@ mlp_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
   // chunk schedule per tile: k1b blocks of W1, 4 of W2, 4 of W3
   const int chunks_per_tile = k1b + 8;
 
-  if (warp == 4) {
+  if (warp == EPI_WARPS) {
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t it = 0;
@@ -126,45 +140,56 @@ mlp_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
         }
       }
     }
-  } else if (warp == 5) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      uint32_t it = 0, a_phase = 0;
-      const uint32_t idesc256 = umma_idesc(TILE_M, 256), idesc16 = umma_idesc(TILE_M, 16);
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        for (int layer = 0; layer < 3; ++layer) {
-          int nkb = layer == 0 ? k1b : 4;
-          uint32_t idesc = layer == 2 ? idesc16 : idesc256;
-          mbar_wait(&sh->a_ready, a_phase);
-          a_phase ^= 1;
-          tc_fence_after();
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
-            int s = it % N_STAGES;
-            uint32_t ph = (it / N_STAGES) & 1;
-            mbar_wait(&sh->w_full[s], ph);
-            tc_fence_after();
-            uint64_t da = umma_desc_sw128(smem_u32(xa + kb * A_BLOCK_BYTES));
-            uint64_t db = umma_desc_sw128(smem_u32(ws + s * W_STAGE_BYTES));
+  } else if (warp == EPI_WARPS + 1) {
+    // ================= MMA issuer (whole warp converged) =================
+    const uint32_t issue = lane == 0 ? 1u : 0u;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    uint32_t it = 0, a_phase = 0;
+    const uint32_t idesc256 = umma_idesc(TILE_M, 256), idesc16 = umma_idesc(TILE_M, 16);
+    const uint64_t a_desc0 = umma_desc_sw128(smem_u32(xa)), w_desc0 = umma_desc_sw128(smem_u32(ws));
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int layer = 0; layer < 3; ++layer) {
+        const int nkb = layer == 0 ? k1b : 4;
+        const uint32_t idesc = layer == 2 ? idesc16 : idesc256;
+        mbar_wait_warp(&sh->a_ready, a_phase);
+        a_phase ^= 1;
+        tc_fence_after();
+#pragma unroll 1
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = __shfl_sync(0xffffffffu, it % N_STAGES, 0);
+          const uint32_t ph = (it / N_STAGES) & 1;
+          mbar_wait_warp(&sh->w_full[s], ph);
+          const uint64_t da = a_desc0 + (uint64_t)(kb * (A_BLOCK_BYTES >> 4));
+          const uint64_t db = w_desc0 + (uint64_t)(s * (W_STAGE_BYTES >> 4));
+          umma_bf16_pred(tmem_u, da, db, idesc, kb ? 1u : 0u, issue);
 #pragma unroll
-            for (int k = 0; k < KB / 16; ++k)  // UMMA_K = 16 bf16 = 32 B = 2 descriptor units
-              umma_bf16(tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-            umma_commit(&sh->w_empty[s]);  // frees the weight stage when these MMAs retire
-          }
-          umma_commit(&sh->mma_done);
+          for (int k = 1; k < KB / 16; ++k)  // UMMA_K = 16 bf16 = 32 B = 2 descriptor units
+            umma_bf16_pred(tmem_u, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u, issue);
+          umma_commit_pred(&sh->w_empty[s], issue);  // frees the weight stage when these MMAs retire
         }
+        umma_commit_pred(&sh->mma_done, issue);
       }
     }
+    __syncwarp();
   } else {
-    // ================= encode + epilogue (128 threads, thread = row) =================
-    const int r = tid;  // row in tile, TMEM lane
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    // ================= encode + epilogue (256 threads, two per row) =================
+    const int r = tid & (TILE_M - 1), half = tid >> 7;  // row in tile = TMEM lane; column half
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t done_phase = 0;
+    // every thread orders its generic-proxy stores before the async proxy, one lane per warp arrives
+    auto signal_a = [&]() {
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->a_ready);
+    };
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int row = t * TILE_M + r;
       const bool live = row < n_rows;
       // ---- encode observation -> bf16 A operand (k1b blocks of [128 x 64], SW128): the maze
-      //      channels are copied from the per-game table, the rest of the row is zeroed and the few
-      //      non-zero elements (two positions, the cheese, six scalars) are stored one by one
+      //      channels are copied from the per-game table, the rest of the row is zeroed (each thread of the
+      //      pair fills half of the row) and the few non-zero elements (two positions, the cheese, six
+      //      scalars) are stored one by one after a barrier
       {
         RowView v;
         const uint4* mt = nullptr;
@@ -175,13 +200,14 @@ mlp_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
           mt = reinterpret_cast<const uint4*>(maze_tab + (size_t)er.game_idx * MAZE_TAB_STRIDE);
           n_maze_pieces = (4 * v.spatial + 7) >> 3;
         }
-        for (int p = 0; p < k1b * 8; ++p) {
+        const int p_half = k1b * 4;
+        for (int p = half * p_half; p < (half + 1) * p_half; ++p) {
           uint4 pk = make_uint4(0, 0, 0, 0);
           if (p < n_maze_pieces) pk = __ldg(mt + p);
           *reinterpret_cast<uint4*>(xa + (p >> 3) * A_BLOCK_BYTES + sw128_offset(r, (p & 7) * 8)) = pk;
         }
-        __syncwarp();  // order the 16-byte fills before the element stores below
-        if (live) {
+        epi_barrier();  // order the 16-byte fills (both threads of a row) before the element stores below
+        if (live && half == 0) {
           const int S = v.spatial;
           put_elem(xa, A_BLOCK_BYTES, r, 4 * S + v.p1, BF16_ONE);
           put_elem(xa, A_BLOCK_BYTES, r, 5 * S + v.p2, BF16_ONE);
@@ -190,8 +216,7 @@ mlp_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
           for (int j = 0; j < 6; ++j) put_elem(xa, A_BLOCK_BYTES, r, 7 * S + j, bf16_bits(obs_elem(v, 7 * S + j)));
         }
       }
-      fence_proxy_async();
-      mbar_arrive(&sh->a_ready);
+      signal_a();
       // ---- hidden layers: D -> +bias, ReLU -> bf16 A operand of the next layer
       for (int layer = 0; layer < 2; ++layer) {
         const float* bias = layer == 0 ? w.b1 : w.b2;
@@ -199,26 +224,33 @@ mlp_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
         done_phase ^= 1;
         tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 16) {
-          float v[16];
-          tmem_ld16(t_lane + c0, v);
+        for (int c64 = half * 128; c64 < half * 128 + 128; c64 += 64) {
+          uint32_t acc[64];  // four loads in flight, one wait
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
-            v[j] = fmaxf(v[j] + b4.x, 0.0f); v[j + 1] = fmaxf(v[j + 1] + b4.y, 0.0f);
-            v[j + 2] = fmaxf(v[j + 2] + b4.z, 0.0f); v[j + 3] = fmaxf(v[j + 3] + b4.w, 0.0f);
+          for (int cc = 0; cc < 64; cc += 16) tmem_ld16_nowait(t_lane + c64 + cc, acc + cc);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int cc = 0; cc < 64; cc += 16) {
+            const int c0 = c64 + cc;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+              v[j] = fmaxf(__uint_as_float(acc[cc + j]) + b4.x, 0.0f);
+              v[j + 1] = fmaxf(__uint_as_float(acc[cc + j + 1]) + b4.y, 0.0f);
+              v[j + 2] = fmaxf(__uint_as_float(acc[cc + j + 2]) + b4.z, 0.0f);
+              v[j + 3] = fmaxf(__uint_as_float(acc[cc + j + 3]) + b4.w, 0.0f);
+            }
+            const int kb = c0 >> 6, col = c0 & 63;
+            uint4 p0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                                  pack_bf16(v[6], v[7]));
+            uint4 p1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
+                                  pack_bf16(v[14], v[15]));
+            *reinterpret_cast<uint4*>(xa + kb * A_BLOCK_BYTES + sw128_offset(r, col)) = p0;
+            *reinterpret_cast<uint4*>(xa + kb * A_BLOCK_BYTES + sw128_offset(r, col + 8)) = p1;
           }
-          int kb = c0 >> 6, col = c0 & 63;
-          uint4 p0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                                pack_bf16(v[6], v[7]));
-          uint4 p1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
-                                pack_bf16(v[14], v[15]));
-          *reinterpret_cast<uint4*>(xa + kb * A_BLOCK_BYTES + sw128_offset(r, col)) = p0;
-          *reinterpret_cast<uint4*>(xa + kb * A_BLOCK_BYTES + sw128_offset(r, col + 8)) = p1;
         }
-        tc_fence_before();
-        fence_proxy_async();
-        mbar_arrive(&sh->a_ready);
+        signal_a();
       }
       // ---- heads: logits p1[0:5], p2[5:10], value[10:12]
       mbar_wait(&sh->mma_done, done_phase);
@@ -227,7 +259,7 @@ mlp_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
       float z[16];
       tmem_ld16(t_lane, z);
       tc_fence_before();
-      if (live) {
+      if (live && half == 0) {
 #pragma unroll
         for (int j = 0; j < 12; ++j) z[j] += __ldg(w.b3 + j);
         float o[12];
@@ -260,7 +292,7 @@ mlp_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 256);
+  if (warp == EPI_WARPS + 1) tmem_dealloc(tmem, 256);
 }
 
 // ---------------------------------------------------------------------------------------
