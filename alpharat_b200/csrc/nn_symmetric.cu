@@ -29,7 +29,9 @@ constexpr int A_BLOCK_BYTES = TILE_M * KB * 2;  // 16 KB
 constexpr int W_STAGE_BYTES = 256 * KB * 2;     // 32 KB
 constexpr int WH_CHUNK_BYTES = 16 * KB * 2;     // 2 KB
 constexpr int N_STAGES = 3;
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;                    // two threads per tile row, 128 output columns each
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = EPI_THREADS + 64;       // + TMA warp + MMA warp
 
 struct Weights {
   const uint8_t* ws;   // ks_blocks x [256 x 64]
@@ -64,30 +66,50 @@ __device__ __forceinline__ float player_elem(const RowView& v, int k, int player
   return 0.0f;
 }
 
-// TMEM accumulator (256 fp32 columns of this thread's lane) -> +bias, ReLU -> bf16 A operand
+// 16 TMEM columns without waiting: several loads are in flight before one wait
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t r[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+
+// TMEM accumulator (this thread's 128 of the 256 fp32 columns of its lane) -> +bias, ReLU -> bf16 A operand
 __device__ __forceinline__ void hidden_epilogue(uint32_t t_addr, const float* __restrict__ bias, uint8_t* dst,
-                                                int r) {
+                                                int r, int half) {
 #pragma unroll 1
-  for (int c0 = 0; c0 < 256; c0 += 16) {
-    float v[16];
-    tmem_ld16(t_addr + c0, v);
+  for (int c64 = half * 128; c64 < half * 128 + 128; c64 += 64) {
+    uint32_t acc[64];  // four loads in flight, one wait
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
-      v[j] = fmaxf(v[j] + b4.x, 0.0f); v[j + 1] = fmaxf(v[j + 1] + b4.y, 0.0f);
-      v[j + 2] = fmaxf(v[j + 2] + b4.z, 0.0f); v[j + 3] = fmaxf(v[j + 3] + b4.w, 0.0f);
+    for (int cc = 0; cc < 64; cc += 16) tmem_ld16_nowait(t_addr + c64 + cc, acc + cc);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int cc = 0; cc < 64; cc += 16) {
+      const int c0 = c64 + cc;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
+        v[j] = fmaxf(__uint_as_float(acc[cc + j]) + b4.x, 0.0f);
+        v[j + 1] = fmaxf(__uint_as_float(acc[cc + j + 1]) + b4.y, 0.0f);
+        v[j + 2] = fmaxf(__uint_as_float(acc[cc + j + 2]) + b4.z, 0.0f);
+        v[j + 3] = fmaxf(__uint_as_float(acc[cc + j + 3]) + b4.w, 0.0f);
+      }
+      const int kb = c0 >> 6, col = c0 & 63;
+      uint4 p0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      uint4 p1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
+                            pack_bf16(v[14], v[15]));
+      *reinterpret_cast<uint4*>(dst + kb * A_BLOCK_BYTES + sw128_offset(r, col)) = p0;
+      *reinterpret_cast<uint4*>(dst + kb * A_BLOCK_BYTES + sw128_offset(r, col + 8)) = p1;
     }
-    int kb = c0 >> 6, col = c0 & 63;
-    uint4 p0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-    uint4 p1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]),
-                          pack_bf16(v[14], v[15]));
-    *reinterpret_cast<uint4*>(dst + kb * A_BLOCK_BYTES + sw128_offset(r, col)) = p0;
-    *reinterpret_cast<uint4*>(dst + kb * A_BLOCK_BYTES + sw128_offset(r, col + 8)) = p1;
   }
 }
 
-// warps 0-3: encode + epilogues (thread t = tile row t = TMEM lane t), warp 4: TMA producer,
-// warp 5: MMA issuer and TMEM owner.
+// warps 0-7: encode + epilogues (threads r and r + 128 own tile row r = TMEM lane r, 128 columns each),
+// warp 8: TMA producer, warp 9: MMA issuer (converged; tcgen05 instructions predicated on lane 0) and TMEM owner.
 __global__ void __launch_bounds__(THREADS, 1)
 symmetric_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict__ n_rows_ptr, int n_rows_arg,
                          const ar_game_pod* __restrict__ games, const uint16_t* __restrict__ maze_tab, Weights w,
@@ -109,11 +131,11 @@ symmetric_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __res
       mbar_init(&sh->w_full[s], 1);
       mbar_init(&sh->w_empty[s], 1);
     }
-    mbar_init(&sh->a_ready, 128);
+    mbar_init(&sh->a_ready, EPI_WARPS);
     mbar_init(&sh->mma_done, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(&sh->tmem_base, 512);
+  if (warp == EPI_WARPS + 1) tmem_alloc(&sh->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -121,7 +143,7 @@ symmetric_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __res
   const int ks = w.ks_blocks;
   const int chunks_per_tile = ks + 1 + 8 + 4 + 4;
 
-  if (warp == 4) {
+  if (warp == EPI_WARPS) {
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t it = 0;
@@ -143,51 +165,62 @@ symmetric_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __res
         }
       }
     }
-  } else if (warp == 5) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+  } else if (warp == EPI_WARPS + 1) {
+    // ================= MMA issuer (whole warp converged) =================
+    {
+      const uint32_t issue = lane == 0 ? 1u : 0u;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
       uint32_t it = 0, a_phase = 0;
       const uint32_t idesc256 = umma_idesc(TILE_M, 256), idesc16 = umma_idesc(TILE_M, 16);
+      const uint64_t w_desc0 = umma_desc_sw128(smem_u32(ws));
       auto chain = [&](uint32_t d_tmem, const uint8_t* a_block, uint32_t idesc, bool first) {
-        int s = it % N_STAGES;
-        uint32_t ph = (it / N_STAGES) & 1;
-        mbar_wait(&sh->w_full[s], ph);
-        tc_fence_after();
-        uint64_t da = umma_desc_sw128(smem_u32(a_block));
-        uint64_t db = umma_desc_sw128(smem_u32(ws + s * W_STAGE_BYTES));
+        const int s = __shfl_sync(0xffffffffu, it % N_STAGES, 0);
+        const uint32_t ph = (it / N_STAGES) & 1;
+        mbar_wait_warp(&sh->w_full[s], ph);
+        const uint64_t da = umma_desc_sw128(smem_u32(a_block));
+        const uint64_t db = w_desc0 + (uint64_t)(s * (W_STAGE_BYTES >> 4));
+        umma_bf16_pred(d_tmem, da, db, idesc, first ? 0u : 1u, issue);
 #pragma unroll
-        for (int k = 0; k < KB / 16; ++k)
-          umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
-        umma_commit(&sh->w_empty[s]);
+        for (int k = 1; k < KB / 16; ++k) umma_bf16_pred(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u, issue);
+        umma_commit_pred(&sh->w_empty[s], issue);
         ++it;
       };
+      auto wait_a = [&]() { mbar_wait_warp(&sh->a_ready, a_phase); a_phase ^= 1; tc_fence_after(); };
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         // stage A: the two encoders into the two accumulators
-        mbar_wait(&sh->a_ready, a_phase); a_phase ^= 1; tc_fence_after();
-        for (int kb = 0; kb < ks; ++kb) chain(tmem, r0 + kb * A_BLOCK_BYTES, idesc256, kb == 0);
-        chain(tmem + 256, r1, idesc256, true);
-        umma_commit(&sh->mma_done);
+        wait_a();
+        for (int kb = 0; kb < ks; ++kb) chain(tmem_u, r0 + kb * A_BLOCK_BYTES, idesc256, kb == 0);
+        chain(tmem_u + 256, r1, idesc256, true);
+        umma_commit_pred(&sh->mma_done, issue);
         // stage B: trunk layer 1 over cat(shared, p)
-        mbar_wait(&sh->a_ready, a_phase); a_phase ^= 1; tc_fence_after();
+        wait_a();
         for (int kb = 0; kb < 8; ++kb)
-          chain(tmem, (kb < 4 ? r0 + kb * A_BLOCK_BYTES : r1 + (kb - 4) * A_BLOCK_BYTES), idesc256, kb == 0);
-        umma_commit(&sh->mma_done);
+          chain(tmem_u, (kb < 4 ? r0 + kb * A_BLOCK_BYTES : r1 + (kb - 4) * A_BLOCK_BYTES), idesc256, kb == 0);
+        umma_commit_pred(&sh->mma_done, issue);
         // stage C: trunk layer 2
-        mbar_wait(&sh->a_ready, a_phase); a_phase ^= 1; tc_fence_after();
-        for (int kb = 0; kb < 4; ++kb) chain(tmem, r0 + kb * A_BLOCK_BYTES, idesc256, kb == 0);
-        umma_commit(&sh->mma_done);
+        wait_a();
+        for (int kb = 0; kb < 4; ++kb) chain(tmem_u, r0 + kb * A_BLOCK_BYTES, idesc256, kb == 0);
+        umma_commit_pred(&sh->mma_done, issue);
         // stage D: heads
-        mbar_wait(&sh->a_ready, a_phase); a_phase ^= 1; tc_fence_after();
-        for (int kb = 0; kb < 4; ++kb) chain(tmem, r1 + kb * A_BLOCK_BYTES, idesc16, kb == 0);
-        umma_commit(&sh->mma_done);
+        wait_a();
+        for (int kb = 0; kb < 4; ++kb) chain(tmem_u, r1 + kb * A_BLOCK_BYTES, idesc16, kb == 0);
+        umma_commit_pred(&sh->mma_done, issue);
       }
+      __syncwarp();
     }
   } else {
     // ================= encode + epilogues =================
-    const int r = tid;
+    const int r = tid & (TILE_M - 1), half = tid >> 7;
     const int player = r & 1;
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t done_phase = 0;
+    // every thread orders its generic-proxy stores before the async proxy, one lane per warp arrives
+    auto signal_a = [&]() {
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->a_ready);
+    };
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int pidx = t * POS_PER_TILE + (r >> 1);
       const bool live = pidx < n_rows;
@@ -203,15 +236,15 @@ symmetric_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __res
           mt = reinterpret_cast<const uint4*>(maze_tab + (size_t)er.game_idx * MAZE_TAB_STRIDE);
           n_maze_pieces = (4 * v.spatial + 7) >> 3;
         }
-        for (int p = 0; p < ks * 8; ++p) {
+        for (int p = half * ks * 4; p < (half + 1) * ks * 4; ++p) {  // each thread of the pair fills half of the row
           uint4 pk = make_uint4(0, 0, 0, 0);
           if (p < n_maze_pieces) pk = __ldg(mt + p);
           *reinterpret_cast<uint4*>(r0 + (p >> 3) * A_BLOCK_BYTES + sw128_offset(r, (p & 7) * 8)) = pk;
         }
 #pragma unroll
-        for (int p = 0; p < 8; ++p) *reinterpret_cast<uint4*>(r1 + sw128_offset(r, p * 8)) = make_uint4(0, 0, 0, 0);
-        __syncwarp();  // order the 16-byte fills before the element stores below
-        if (live) {
+        for (int p = 0; p < 4; ++p) *reinterpret_cast<uint4*>(r1 + sw128_offset(r, (half * 4 + p) * 8)) = make_uint4(0, 0, 0, 0);
+        epi_barrier();  // order the 16-byte fills (both threads of a row) before the element stores below
+        if (live && half == 0) {
           const int S = v.spatial;
           for (uint64_t c = v.cheese; c; c &= c - 1) put_elem(r0, A_BLOCK_BYTES, r, 4 * S + (__ffsll((long long)c) - 1), BF16_ONE);
           put_elem(r0, A_BLOCK_BYTES, r, 5 * S, bf16_bits(v.progress));
@@ -220,23 +253,23 @@ symmetric_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __res
           put_elem(r1, A_BLOCK_BYTES, r, S + 1, bf16_bits(player_elem(v, S + 1, player)));
         }
       }
-      fence_proxy_async();
-      mbar_arrive(&sh->a_ready);
+      signal_a();
       // stage A results: shared -> r0, p -> r1
       mbar_wait(&sh->mma_done, done_phase); done_phase ^= 1; tc_fence_after();
-      hidden_epilogue(t_lane, w.bs, r0, r);
-      hidden_epilogue(t_lane + 256, w.bp, r1, r);
-      tc_fence_before(); fence_proxy_async(); mbar_arrive(&sh->a_ready);
+      hidden_epilogue(t_lane, w.bs, r0, r, half);
+      hidden_epilogue(t_lane + 256, w.bp, r1, r, half);
+      signal_a();
       // stage B result: t -> r0
       mbar_wait(&sh->mma_done, done_phase); done_phase ^= 1; tc_fence_after();
-      hidden_epilogue(t_lane, w.bt1, r0, r);
-      tc_fence_before(); fence_proxy_async(); mbar_arrive(&sh->a_ready);
+      hidden_epilogue(t_lane, w.bt1, r0, r, half);
+      signal_a();
       // stage C result: h -> r1
       mbar_wait(&sh->mma_done, done_phase); done_phase ^= 1; tc_fence_after();
-      hidden_epilogue(t_lane, w.bt2, r1, r);
-      tc_fence_before(); fence_proxy_async(); mbar_arrive(&sh->a_ready);
+      hidden_epilogue(t_lane, w.bt2, r1, r, half);
+      signal_a();
       // stage D: heads.  z[0:5] = Wa_pol.h_i, z[5] = Wa_val.h_i, z[6:11] = Wb_pol.h_i, z[11] = Wb_val.h_i
       mbar_wait(&sh->mma_done, done_phase); done_phase ^= 1; tc_fence_after();
+      if (half != 0) { tc_fence_before(); continue; }  // the heads are 16 columns: the first thread of a row finishes them
       float z[16];
       tmem_ld16(t_lane, z);
       tc_fence_before();
@@ -275,7 +308,7 @@ symmetric_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __res
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 512);
+  if (warp == EPI_WARPS + 1) tmem_dealloc(tmem, 512);
 }
 
 struct Model : LeafEvaluator {
