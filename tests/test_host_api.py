@@ -282,3 +282,37 @@ def test_run_cuda_sampling_batch_protocol(oracle, tmp_path):
     assert [resolve_sampling_device(d) for d in ("auto", "cuda", "cuda:3", "b200", 5)] == [0, 0, 3, 0, 5]
     with pytest.raises(ValueError):
         resolve_sampling_device("coreml")
+
+
+def test_cuda_self_play_hands_cache_size_to_the_engine(oracle, tmp_path):
+    """`cache_size` (rust_self_play, sampling/bindings.rs:299) reaches `ar_engine_set_eval_cache` whenever an
+    evaluator is loaded, and the statistics come straight from the engine (no host-side bookkeeping)."""
+    calls = []
+
+    class StubEngine:  # the surface cuda_self_play uses; play itself is the oracle's (CPU-only box)
+        has_evaluator = True
+
+        def set_eval_cache(self, n):
+            calls.append(n)
+
+        def selfplay(self, pods, cfg, seeds, progress=None):
+            summ, pos, stride, st = oracle_selfplay(oracle, pods, cfg, seeds, n_threads=2)
+            st.cache_hits, st.cache_misses = 7, 5
+            return summ, pos, stride, st
+
+        def close(self):
+            calls.append("closed")
+
+    eng = StubEngine()
+    stats = ab.cuda_self_play(width=5, height=5, cheese_count=5, max_turns=20, num_games=3, simulations=30,
+                              output_dir=str(tmp_path / "g"), cache_size=2048, seed=3, engine=eng)
+    assert calls == [2048]  # a caller-owned engine is configured but not closed
+    assert (stats.cache_hits, stats.cache_misses, round(stats.cache_hit_rate, 4)) == (7, 5, round(7 / 12, 4))
+    assert len(list((tmp_path / "g").glob("bundle_*.npz"))) == 1
+    eng.has_evaluator = False
+    ab.cuda_self_play(width=5, height=5, cheese_count=5, max_turns=20, num_games=1, simulations=10,
+                      output_dir=None, cache_size=2048, seed=3, engine=eng)
+    assert calls == [2048]  # uniform priors: there is nothing to cache
+    with pytest.raises(ValueError):
+        ab.cuda_self_play(width=5, height=5, cheese_count=5, max_turns=20, num_games=1, simulations=10,
+                          output_dir=None, cache_size=-1, engine=eng)
