@@ -359,6 +359,7 @@ struct NnParams {
   uint32_t cache_mask;
   int max_iters;            // gather / backup rounds a slot may chain inside one step
   uint4* board_store;       // [n_slots][SM_TP / 16]: move table + maze of the slot's game, built once per game
+  int slot_begin, slot_end; // the slots this launch steps (the slots are split into groups that alternate)
 };
 
 __global__ void nn_init_slots_kernel(SlotState* slots, int n) {
@@ -377,8 +378,8 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
   int lane = threadIdx.x & 31;
   asm volatile("" : "+r"(lane));
   const int wib = threadIdx.x >> 5;
-  const int slot = blockIdx.x * 4 + wib;
-  if (slot >= p.n_slots) return;
+  const int slot = q.slot_begin + blockIdx.x * 4 + wib;
+  if (slot >= q.slot_end) return;
   SlotState* sp_g = q.slots + slot;
   if (sp_g->phase == PH_DONE) return;
 
@@ -728,6 +729,8 @@ struct ar_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t stream2 = nullptr;              // second slot group of the NN-guided loop
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   // per-slot storage
   NodeRec* pools = nullptr;
@@ -959,6 +962,9 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
     if (_e != cudaSuccess) return fail(AR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
   } while (0)
   CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+  CKC(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   CKC(cudaEventCreate(&e->ev0));
   CKC(cudaEventCreate(&e->ev1));
   CKC(cudaMalloc(&e->pools, (size_t)e->n_slots * (size_t)pn * sizeof(NodeRec)));
@@ -993,6 +999,9 @@ void ar_engine_destroy(ar_engine* e) {
   if (e->h_progress) cudaFreeHost(e->h_progress);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->stream2) cudaStreamDestroy(e->stream2);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -1084,7 +1093,7 @@ static ar_status ensure_nn_buffers(ar_engine* e) {
   CK(cudaMalloc(&e->d_tp_store, max_rows * sizeof(TpEntry)));
   CK(cudaMalloc(&e->d_queue, max_rows * sizeof(EvalRow)));
   CK(cudaMalloc(&e->d_queue_out, max_rows * 12 * sizeof(float)));
-  CK(cudaMalloc(&e->d_n_rows, 2 * sizeof(uint32_t)));
+  CK(cudaMalloc(&e->d_n_rows, 4 * sizeof(uint32_t)));  // [0] queue length of group 0, [1] done slots, [2] queue length of group 1
   CK(cudaMalloc(&e->d_key_store, max_rows * sizeof(GPack)));
   CK(cudaMalloc(&e->d_board_store, (size_t)e->n_slots * SM_TP));
   return AR_OK;
@@ -1132,27 +1141,56 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
       q.cache_mask = e->cache_entries - 1;
       CK(cudaMemsetAsync(e->d_cache, 0, (size_t)slots * e->cache_entries * sizeof(CacheEnt), e->stream));
     }
-    CK(cudaMemsetAsync(e->d_n_rows, 0, 2 * sizeof(uint32_t), e->stream));
+    CK(cudaMemsetAsync(e->d_n_rows, 0, 4 * sizeof(uint32_t), e->stream));
     nn_init_slots_kernel<<<(slots + 127) / 128, 128, 0, e->stream>>>(e->d_slots, slots);
     CK(cudaGetLastError());
     e->launches += 1;
-    // 32 steps (queue reset, tree step, evaluator) are captured once into a CUDA graph and replayed: the step
-    // kernels are short (0.3-1 ms) and depend on each other, so launch gaps would otherwise show.  The host
-    // reads one counter per replay to know when every game is finished.
+    // With more slots than one wave of warps (148 SMs x 28), the slots are split into two groups that step on
+    // two streams: a step is bulk-synchronous (tree kernel, then evaluator), so while one group's stragglers
+    // finish or its leaves are being scored, the other group's tree kernel fills the SMs (config 3, 16384
+    // slots: +7 %).  A single wave is better left whole (4096 slots: two groups of 2048 cost 9 %).  Each
+    // group has its own evaluation queue; games, trees, caches and counters are shared arrays indexed by
+    // the global slot.
+    const int n_groups = slots >= 8192 ? 2 : 1;
+    NnParams qs[2] = {q, q};
+    cudaStream_t streams[2] = {e->stream, e->stream2};
+    for (int g = 0; g < n_groups; ++g) {
+      const int s0 = n_groups == 2 ? ((slots / 2 + 3) & ~3) : slots;
+      qs[g].slot_begin = g ? s0 : 0;
+      qs[g].slot_end = g ? slots : s0;
+      qs[g].rows = e->d_queue + (size_t)qs[g].slot_begin * e->batch_cap;
+      qs[g].nn_out = e->d_queue_out + (size_t)qs[g].slot_begin * e->batch_cap * 12;
+      qs[g].n_rows = e->d_n_rows + (g ? 2 : 0);
+      qs[g].max_rows = (uint32_t)((size_t)(qs[g].slot_end - qs[g].slot_begin) * e->batch_cap);
+    }
+    // 32 steps (queue reset, tree step, evaluator; both groups) are captured once into a CUDA graph and
+    // replayed: the step kernels are short (0.3-1 ms) and depend on each other, so launch gaps would otherwise
+    // show.  The host reads one counter per replay to know when every game is finished.
     const int check_every = 32;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     cudaError_t cap = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
     if (cap == cudaSuccess) {
       cudaError_t in_cap = cudaSuccess;
+      if (n_groups == 2) {
+        in_cap = cudaEventRecord(e->ev_fork, e->stream);
+        if (in_cap == cudaSuccess) in_cap = cudaStreamWaitEvent(e->stream2, e->ev_fork, 0);
+      }
       for (int it = 0; it < check_every && in_cap == cudaSuccess; ++it) {
-        in_cap = cudaMemsetAsync(e->d_n_rows, 0, sizeof(uint32_t), e->stream);
-        if (in_cap != cudaSuccess) break;
-        nn_step_kernel<<<blocks, 128, smem, e->stream>>>(p, q);
-        in_cap = cudaGetLastError();
-        if (in_cap != cudaSuccess) break;
-        in_cap = e->eval->forward(e->d_queue, e->d_n_rows, (int)q.max_rows, p.games, e->d_maze_tab, e->d_queue_out,
-                                  e->d_error, e->stream);
+        for (int g = 0; g < n_groups && in_cap == cudaSuccess; ++g) {
+          const NnParams& qg = qs[g];
+          in_cap = cudaMemsetAsync(qg.n_rows, 0, sizeof(uint32_t), streams[g]);
+          if (in_cap != cudaSuccess) break;
+          nn_step_kernel<<<(qg.slot_end - qg.slot_begin + 3) / 4, 128, smem, streams[g]>>>(p, qg);
+          in_cap = cudaGetLastError();
+          if (in_cap != cudaSuccess) break;
+          in_cap = e->eval->forward(qg.rows, qg.n_rows, (int)qg.max_rows, p.games, e->d_maze_tab,
+                                    const_cast<float*>(qg.nn_out), e->d_error, streams[g]);
+        }
+      }
+      if (n_groups == 2 && in_cap == cudaSuccess) {
+        in_cap = cudaEventRecord(e->ev_join, e->stream2);
+        if (in_cap == cudaSuccess) in_cap = cudaStreamWaitEvent(e->stream, e->ev_join, 0);
       }
       cap = cudaStreamEndCapture(e->stream, &graph);
       if (in_cap != cudaSuccess) cap = in_cap;
@@ -1166,7 +1204,7 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
     ar_status loop_status = AR_OK;
     for (;;) {
       cudaError_t le = cudaGraphLaunch(gexec, e->stream);
-      e->launches += 2 * check_every;
+      e->launches += 2 * check_every * n_groups;
       e->nn_steps += check_every;
       uint32_t h[2] = {0, 0};
       int herr = 0;
