@@ -23,6 +23,8 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
+
 #include "nn_common.cuh"
 
 namespace ar {
@@ -94,7 +96,8 @@ mlp_forward_kernel(const EvalRow* __restrict__ rows, const uint32_t* __restrict_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* xa = smem;                                  // A operand / hidden activations
-  uint8_t* ws = smem + w.k1_blocks * A_BLOCK_BYTES;    // weight stages
+  // the buffer holds the encoded observation (k1_blocks K-blocks) and later the 256 hidden activations (4)
+  uint8_t* ws = smem + (w.k1_blocks > 4 ? w.k1_blocks : 4) * A_BLOCK_BYTES;    // weight stages
   MlpSmem* sh = reinterpret_cast<MlpSmem*>(ws + N_STAGES * W_STAGE_BYTES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -338,7 +341,7 @@ int MlpModel::load(const ar_tensor_desc* t, int n, int width, int height, std::s
   CKN(cudaMemcpy(d_w2, i2.data(), i2.size(), cudaMemcpyHostToDevice));
   CKN(cudaMemcpy(d_w3, i3.data(), i3.size(), cudaMemcpyHostToDevice));
   CKN(cudaMemcpy(d_b, ball.data(), ball.size() * 4, cudaMemcpyHostToDevice));
-  smem_bytes = (size_t)k1_blocks * A_BLOCK_BYTES + N_STAGES * W_STAGE_BYTES + sizeof(MlpSmem) + 1024;
+  smem_bytes = (size_t)std::max(k1_blocks, 4) * A_BLOCK_BYTES + N_STAGES * W_STAGE_BYTES + sizeof(MlpSmem) + 1024;
   CKN(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   int dev = 0;
   CKN(cudaGetDevice(&dev));

@@ -77,6 +77,23 @@ def test_mlp_forward_matches_reference(n):
     assert (v1 >= 0).all() and (v2 >= 0).all()
 
 
+@pytest.mark.parametrize("w,h,n", [(5, 5, 300), (4, 3, 70), (6, 5, 129)])
+def test_mlp_forward_small_boards(w, h, n):
+    """Boards whose observation needs fewer K-blocks than the 256-wide hidden layers (5x5: 3, 4x3: 2): the operand
+    buffer is sized by the larger of the two.  Checked against the fp32 restatement of PyRatMLP (validated against
+    the real reference at 7x7 in test_oracle_golden.py) on the device encoder's observations."""
+    base = random_positions(40, w, h, seed=11)
+    specs = [base[i % 40] for i in range(n)]
+    sd = make_mlp_state_dict(5, 7 * w * h + 6)
+    with Engine(concurrent_games=4, max_turns=120) as eng:
+        eng.load_weights(N.AR_ARCH_MLP, w, h, sd)
+        pods = pods_array(specs)
+        obs = eng.encode(pods)
+        out = eng.nn_forward(pods)
+    _check_vs_fp32(out, mlp_forward(sd, obs), 2e-2, 3e-2, f"mlp {w}x{h} fp32")
+    _check_vs_fp32(out, mlp_forward(sd, obs, emulate_bf16=True), 2e-3, 4e-3, f"mlp {w}x{h} bf16 restatement")
+
+
 def _check_vs_fp32(out, ref, tol_p, tol_v, tag):
     p1, p2, v1, v2 = out
     assert np.abs(p1 - ref[0]).max() <= tol_p, (tag, float(np.abs(p1 - ref[0]).max()))

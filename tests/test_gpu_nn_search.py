@@ -174,3 +174,33 @@ def test_eval_cache_changes_nothing_but_the_evaluator_load(oracle, arch, make_sd
     assert cached[3].cache_hits > 0 and cached[3].cache_hits == again[3].cache_hits
     assert tiny[3].cache_hits <= cached[3].cache_hits
     assert off[3].cache_hits == 0 and off[3].cache_misses == 0
+
+
+def test_two_slot_groups_play_the_same_games():
+    """With 8192 or more resident trees the NN-guided loop steps two slot groups on two streams (each with its
+    own evaluation queue).  Scheduling must not leak into results: the records equal those of a 4096-tree
+    engine (one group, the path the oracle tests pin) game for game."""
+    n = 8192
+    specs = make_games(n, width=5, height=5, cheese_count=5, max_turns=3, first_index=7000)
+    pods = pods_array(specs)
+    sd = make_mlp_state_dict(4, 7 * 25 + 6)
+    cfg = search_cfg(simulations=24, batch_size=8, c_puct=1.5, fpu_reduction=0.2, force_k=2.0)
+    seeds = [5 * i + 1 for i in range(n)]
+    runs = []
+    for conc, cache in ((4096, 0), (8192, 0), (8192, 64)):
+        with Engine(concurrent_games=conc, max_turns=3, max_batch_size=8, max_simulations=24, pool_nodes=128) as eng:
+            eng.load_weights(N.AR_ARCH_MLP, 5, 5, sd)
+            eng.set_eval_cache(cache)
+            runs.append(eng.selfplay(pods, cfg, seeds))
+    ref_s, ref_p, stride, ref_st = runs[0]
+    for s, p, _, st in runs[1:]:
+        assert (st.total_positions, st.total_simulations, st.total_nn_evals, st.total_terminals, st.total_collisions) == (
+            ref_st.total_positions, ref_st.total_simulations, ref_st.total_nn_evals, ref_st.total_terminals,
+            ref_st.total_collisions)
+        for g in range(0, n, 7):
+            assert s[g].n_positions == ref_s[g].n_positions and s[g].final_p1_score == ref_s[g].final_p1_score
+            for t in range(s[g].n_positions):
+                a, b = p[g * stride + t], ref_p[g * stride + t]
+                assert (a.action_p1, a.action_p2) == (b.action_p1, b.action_p2)
+                assert_result_equal(a.search, b.search, f"game {g} turn {t}")
+    assert runs[2][3].cache_hits + runs[2][3].cache_misses == ref_st.total_nn_evals
