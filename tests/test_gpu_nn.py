@@ -155,6 +155,26 @@ def test_cnn_forward_matches_reference(tag, blocks, w, h, n):
                    f"cnn {tag} {w}x{h} n={n}")
 
 
+@pytest.mark.parametrize("w,h,n", [(8, 8, 37), (6, 4, 100), (4, 4, 90), (4, 7, 61)])
+def test_cnn_and_symmetric_forward_other_boards(w, h, n):
+    """Board geometries the golden files do not cover: one position per tile (8x8), non-square boards, five
+    positions per tile (4x4).  Reference = the numpy restatements of PyRatCNN / SymmetricMLP (validated against
+    the real reference at 5x5 and 7x7 in test_oracle_golden.py) on the device encoder's observations."""
+    base = random_positions(40, w, h, seed=21)
+    specs = [base[i % 40] for i in range(n)]
+    pods = pods_array(specs)
+    with Engine(concurrent_games=4, max_turns=120) as eng:
+        obs = eng.encode(pods)
+        for blocks in (("res", "res", "gpool"), ("gpool", "res")):
+            sd = make_cnn_state_dict(7, blocks)
+            eng.load_weights(N.AR_ARCH_CNN, w, h, sd)
+            _check_vs_fp32(eng.nn_forward(pods), cnn_forward(sd, obs, w, h), 3e-2, 5e-2, f"cnn {blocks} {w}x{h}")
+        if 5 * w * h + 1 <= 256:
+            sd = make_symmetric_state_dict(8, w, h)
+            eng.load_weights(N.AR_ARCH_SYMMETRIC, w, h, sd)
+            _check_vs_fp32(eng.nn_forward(pods), symmetric_forward(sd, obs, w, h), 3e-2, 5e-2, f"symmetric {w}x{h}")
+
+
 def test_unsupported_evaluator_shapes_fail_loudly():
     sd = make_symmetric_state_dict(2, 7, 7, hidden=128)
     with Engine(concurrent_games=4, max_turns=120) as eng:
