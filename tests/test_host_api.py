@@ -316,3 +316,57 @@ def test_cuda_self_play_hands_cache_size_to_the_engine(oracle, tmp_path):
     with pytest.raises(ValueError):
         ab.cuda_self_play(width=5, height=5, cheese_count=5, max_turns=20, num_games=1, simulations=10,
                           output_dir=None, cache_size=-1, engine=eng)
+
+
+REFERENCE = Path("/root/reference")
+
+
+@pytest.mark.skipif(not (REFERENCE / "alpharat" / "data" / "loader.py").exists(),
+                    reason="the reference tree is only mounted in the build container")
+def test_bundles_load_with_the_reference_loader(oracle, tmp_path):
+    """Drop-in check of the bundle format with the reference's own consumer: `load_game_bundle`
+    (alpharat/data/loader.py:114-130, the loader behind sharding / training; the reference tests it against
+    Rust-written bundles in tests/data/test_rust_bundle_parity.py) reads the files `write_bundles` produced and
+    returns the games that were played.  Only loader.py and types.py are imported (the package __init__ needs the
+    third-party engine)."""
+    import importlib
+    import sys
+    import types
+
+    saved = {k: sys.modules.get(k) for k in ("alpharat", "alpharat.data", "alpharat.data.types", "alpharat.data.loader")}
+    try:
+        for name, path in (("alpharat", REFERENCE / "alpharat"), ("alpharat.data", REFERENCE / "alpharat" / "data")):
+            pkg = types.ModuleType(name)
+            pkg.__path__ = [str(path)]
+            sys.modules[name] = pkg
+        loader = importlib.import_module("alpharat.data.loader")
+
+        n = 5
+        specs = (make_games(3, width=5, height=5, cheese_count=5, max_turns=30)
+                 + make_games(2, width=7, height=5, cheese_count=6, max_turns=20, maze_type="classic", first_index=9))
+        pods = pods_array(specs)
+        summ, pos, stride, st = oracle_selfplay(oracle, pods, search_cfg(simulations=40), list(range(n)), n_threads=2)
+        paths = write_bundles(tmp_path / "games", specs[:3], summ, pos, stride, max_games_per_bundle=8)
+        assert len(paths) == 1 and loader.is_bundle_file(paths[0])
+        games = loader.load_game_bundle(paths[0])
+        assert len(games) == 3
+        for g, game in enumerate(games):
+            assert (game.width, game.height, game.max_turns) == (5, 5, 30)
+            assert len(game.positions) == summ[g].n_positions
+            assert (game.final_p1_score, game.final_p2_score) == (summ[g].final_p1_score, summ[g].final_p2_score)
+            assert np.array_equal(game.maze, maze_array(specs[g]))
+            assert sorted(map(tuple, np.argwhere(game.initial_cheese)[:, ::-1].tolist())) == sorted(specs[g].cheese)
+            for t, p in enumerate(game.positions):
+                r = pos[g * stride + t]
+                assert (tuple(p.p1_pos), tuple(p.p2_pos)) == ((r.p1_x, r.p1_y), (r.p2_x, r.p2_y))
+                assert (p.action_p1, p.action_p2, p.turn) == (r.action_p1, r.action_p2, r.turn)
+                assert np.array_equal(np.asarray(p.policy_p1, np.float32), np.asarray(list(r.search.policy_p1), np.float32))
+                assert np.array_equal(np.asarray(p.visit_counts_p2, np.float32),
+                                      np.asarray(list(r.search.visit_counts_p2), np.float32))
+                assert np.float32(p.value_p1) == np.float32(r.search.value_p1)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
