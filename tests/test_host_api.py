@@ -370,3 +370,89 @@ def test_bundles_load_with_the_reference_loader(oracle, tmp_path):
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+@pytest.mark.skipif(not REFERENCE.exists(), reason="the reference tree is only mounted in the build container")
+def test_interface_surface_matches_the_reference_sources():
+    """The mirrored interface is compared with the reference's own sources (parsed, not imported: the Rust
+    extension modules are absent): keywords and defaults of `rust_self_play` / `rust_mcts_search`, the fields and
+    defaults of `RustMCTSConfig`, the fields of `SearchResult`, the getters of the `SelfPlayStats` pyclass."""
+    import ast
+    import dataclasses
+    import re
+
+    def pyo3_signature(path, fn):
+        src = (REFERENCE / path).read_text()
+        m = re.search(r"#\[pyo3\(signature = \((.*?)\)\)\]\s*(?:#\[[^\]]*\]\s*)*fn " + fn + r"\b", src, re.S)
+        assert m, f"{fn} not found in {path}"
+        out = {}
+        for part in m.group(1).split(","):
+            part = part.strip()
+            if part and part != "*":
+                name, _, default = part.partition("=")
+                out[name.strip()] = default.strip() or None
+        return out
+
+    def same_default(rust, py):
+        if rust in (None, "None"):
+            return True  # required keyword, or None
+        if rust in ("true", "false"):
+            return py is (rust == "true")
+        if rust.startswith('"'):
+            return py == rust.strip('"') or (rust == '"auto"' and py == "cuda")  # device: a GPU, not an ORT provider
+        return float(rust) == float(py)
+
+    sig = inspect.signature(ab.cuda_self_play).parameters
+    for name, default in pyo3_signature("crates/alpharat-sampling/src/bindings.rs", "rust_self_play").items():
+        assert name in sig, f"cuda_self_play lacks {name}"
+        py_default = sig[name].default
+        if default is None:
+            assert py_default is inspect.Parameter.empty or name == "output_dir", name
+        else:
+            assert same_default(default, py_default), (name, default, py_default)
+
+    # CudaSearcher mirrors RustSearcher.__init__ (alpharat/mcts/searcher.py:43-59): same names, order and defaults
+    # (predict_fn is replaced by checkpoint=), which in turn forwards to rust_mcts_search's keywords
+    search = pyo3_signature("crates/alpharat-mcts/src/bindings.rs", "rust_mcts_search")
+    tree = ast.parse((REFERENCE / "alpharat/mcts/searcher.py").read_text())
+    cls = next(n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == "RustSearcher")
+    init = next(s for s in cls.body if isinstance(s, ast.FunctionDef) and s.name == "__init__")
+    ref_args = [a.arg for a in init.args.args[1:]]
+    ref_defaults = dict(zip(ref_args[len(ref_args) - len(init.args.defaults):], map(ast.literal_eval, init.args.defaults)))
+    ctor = inspect.signature(ab.CudaSearcher.__init__).parameters
+    ours = [n for n in ctor if n != "self"]
+    shared = [a for a in ref_args if a != "predict_fn"]
+    assert [n for n in ours if n in shared] == shared  # same relative order (positional call sites keep working)
+    assert ours[:4] == ref_args[:4] == ["simulations", "c_puct", "force_k", "fpu_reduction"]
+    for name in shared:
+        if name in ref_defaults:
+            assert ctor[name].default == ref_defaults[name], name
+        else:
+            assert ctor[name].default is inspect.Parameter.empty, name
+        assert name in search  # every constructor keyword is a keyword of the Rust binding
+
+    tree = ast.parse((REFERENCE / "alpharat/mcts/config.py").read_text())
+    cls = next(n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == "RustMCTSConfig")
+    ref_fields = {s.target.id: ast.literal_eval(s.value) for s in cls.body
+                  if isinstance(s, ast.AnnAssign) and s.value is not None}
+    assert ref_fields.pop("backend") == "rust"
+    ours = ab.CudaMCTSConfig()
+    for name, default in ref_fields.items():
+        assert getattr(ours, name) == default and getattr(ab.RustMCTSConfig(), name) == default, name
+    for method in ("for_evaluation", "build_searcher", "build_agent"):
+        assert any(isinstance(s, ast.FunctionDef) and s.name == method for s in cls.body) and hasattr(ours, method)
+
+    tree = ast.parse((REFERENCE / "alpharat/mcts/result.py").read_text())
+    cls = next(n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == "SearchResult")
+    assert [s.target.id for s in cls.body if isinstance(s, ast.AnnAssign)] == [f.name for f in dataclasses.fields(ab.SearchResult)]
+
+    src = (REFERENCE / "crates/alpharat-sampling/src/bindings.rs").read_text()
+    stats_impl = src[src.index("impl PySelfPlayStats"):src.index("impl PySelfPlayProgress")] \
+        if "impl PySelfPlayProgress" in src else src[src.index("impl PySelfPlayStats"):]
+    getters = re.findall(r"#\[getter\]\s*fn (\w+)", stats_impl)
+    assert len(getters) >= 20
+    from alpharat_b200.selfplay import SelfPlayStats
+
+    st = SelfPlayStats(N.Stats())
+    missing = [g for g in getters if not hasattr(st, g)]
+    assert missing == [], missing
