@@ -446,6 +446,22 @@ def test_interface_surface_matches_the_reference_sources():
     cls = next(n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == "SearchResult")
     assert [s.target.id for s in cls.body if isinstance(s, ast.AnnAssign)] == [f.name for f in dataclasses.fields(ab.SearchResult)]
 
+    # run_cuda_sampling / CudaSamplingMetrics against alpharat/data/rust_sampling.py
+    from alpharat_b200.sampling import CudaSamplingMetrics, run_cuda_sampling
+
+    tree = ast.parse((REFERENCE / "alpharat/data/rust_sampling.py").read_text())
+    fn = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "run_rust_sampling")
+    ref_kw = [a.arg for a in fn.args.kwonlyargs]
+    ref_kw_defaults = {a.arg: ast.literal_eval(d) for a, d in zip(fn.args.kwonlyargs, fn.args.kw_defaults) if d is not None}
+    ours_kw = inspect.signature(run_cuda_sampling).parameters
+    assert [k for k in ref_kw if k not in ours_kw] == []
+    for k, d in ref_kw_defaults.items():
+        assert ours_kw[k].default == d or k == "device", k  # device: "cuda" here, an ORT provider name there
+    cls = next(n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == "RustSamplingMetrics")
+    assert [s.target.id for s in cls.body if isinstance(s, ast.AnnAssign)] == list(CudaSamplingMetrics.__dataclass_fields__)
+    ref_props = [s.name for s in cls.body if isinstance(s, ast.FunctionDef)]
+    assert ref_props and all(isinstance(getattr(CudaSamplingMetrics, p), property) for p in ref_props)
+
     src = (REFERENCE / "crates/alpharat-sampling/src/bindings.rs").read_text()
     stats_impl = src[src.index("impl PySelfPlayStats"):src.index("impl PySelfPlayProgress")] \
         if "impl PySelfPlayProgress" in src else src[src.index("impl PySelfPlayStats"):]
