@@ -24,7 +24,7 @@ from dataclasses import dataclass
 from pathlib import Path
 from typing import Any
 
-from .selfplay import SelfPlayProgress, cuda_self_play
+from .selfplay import SelfPlayProgress, cuda_self_play, resolve_sampling_device
 
 logger = logging.getLogger(__name__)
 
@@ -33,19 +33,6 @@ _SEARCH_FIELDS = (
     "collision_limit_min", "collision_limit_max", "collision_scaling_start", "collision_scaling_end",
     "collision_scaling_power",
 )
-
-
-def resolve_sampling_device(device: str | int) -> int:
-    """GPU ordinal for a user-facing device name (rust_sampling.py:23-32 maps to ORT providers instead)."""
-    if isinstance(device, int):
-        return device
-    d = device.lower()
-    if d in ("auto", "cuda", "b200", "gpu", "tensorrt"):
-        return 0
-    for prefix in ("cuda:", "b200:", "gpu:"):
-        if d.startswith(prefix) and d[len(prefix):].isdigit():
-            return int(d[len(prefix):])
-    raise ValueError(f"backend cuda cannot run on device {device!r} (expected 'cuda', 'cuda:<n>' or an int)")
 
 
 def resolve_training_device(device: str | int) -> str:

@@ -20,6 +20,19 @@ from .engine import Engine, search_cfg
 from .games import GameSpec, make_games, pods_array
 
 
+def resolve_sampling_device(device: str | int) -> int:
+    """GPU ordinal for a user-facing device name (rust_sampling.py:23-32 maps to ORT providers instead)."""
+    if isinstance(device, int):
+        return device
+    d = device.lower()
+    if d in ("auto", "cuda", "b200", "gpu", "tensorrt"):
+        return 0
+    for prefix in ("cuda:", "b200:", "gpu:"):
+        if d.startswith(prefix) and d[len(prefix):].isdigit():
+            return int(d[len(prefix):])
+    raise ValueError(f"backend cuda cannot run on device {device!r} (expected 'cuda', 'cuda:<n>' or an int)")
+
+
 class SelfPlayProgress:
     """Live counters, readable from another thread while `cuda_self_play` runs."""
 
@@ -153,7 +166,7 @@ def cuda_self_play(
                      collision_scaling_end=collision_scaling_end, collision_scaling_power=collision_scaling_power)
     base_seed = seed if seed is not None else secrets.randbits(63)
     seeds = [(base_seed + i) & ((1 << 64) - 1) for i in range(len(specs))]
-    dev = 0 if isinstance(device, str) else int(device)
+    dev = resolve_sampling_device(device)
     own = engine is None
     if own:
         mt = max([s.max_turns for s in specs] + [1])

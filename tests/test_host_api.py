@@ -316,6 +316,9 @@ def test_cuda_self_play_hands_cache_size_to_the_engine(oracle, tmp_path):
     with pytest.raises(ValueError):
         ab.cuda_self_play(width=5, height=5, cheese_count=5, max_turns=20, num_games=1, simulations=10,
                           output_dir=None, cache_size=-1, engine=eng)
+    with pytest.raises(ValueError, match="device"):  # an ORT provider name is not a GPU
+        ab.cuda_self_play(width=5, height=5, cheese_count=5, max_turns=20, num_games=1, simulations=10,
+                          output_dir=None, device="coreml", engine=eng)
 
 
 REFERENCE = Path("/root/reference")
