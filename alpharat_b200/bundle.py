@@ -39,32 +39,56 @@ def _cheese_mask(bits: np.ndarray, h: int, w: int) -> np.ndarray:
     return unpacked.reshape(*bits.shape[:-1], h, w).astype(np.bool_)
 
 
-def build_bundle_arrays(specs: Sequence[GameSpec], summaries, pos_np: np.ndarray, idx: Sequence[int]) -> dict:
+def summaries_as_numpy(summaries, n_games: int) -> np.ndarray:
+    """View the ctypes `ar_game_summary` array as a structured numpy array [n_games]."""
+    return np.frombuffer(summaries, dtype=np.dtype(N.GameSummary), count=n_games)
+
+
+_MAZE_CACHE: dict = {}
+
+
+def _maze_cached(spec: GameSpec) -> np.ndarray:
+    """`maze_array` memoised on the layout (self-play batches share one maze, or a handful)."""
+    key = (spec.width, spec.height, tuple(map(tuple, spec.walls)), tuple(map(tuple, spec.mud)))
+    m = _MAZE_CACHE.get(key)
+    if m is None:
+        if len(_MAZE_CACHE) > 4096:
+            _MAZE_CACHE.clear()
+        m = _MAZE_CACHE[key] = maze_array(spec).astype(np.int8)
+    return m
+
+
+def build_bundle_arrays(specs: Sequence[GameSpec], summaries, pos_np: np.ndarray, idx: Sequence[int],
+                        summ_np: np.ndarray | None = None) -> dict:
+    """The 26 arrays of one bundle for the games `idx` (all of one board size).  Vectorised over games and
+    positions: the only per-game Python work is the maze lookup and the initial cheese list."""
+    idx = np.asarray(idx, dtype=np.int64)
+    if summ_np is None:
+        summ_np = summaries_as_numpy(summaries, int(idx.max()) + 1)
     h, w = specs[idx[0]].height, specs[idx[0]].width
     for i in idx:
         if (specs[i].height, specs[i].width) != (h, w):
             raise ValueError(f"game {i} has dimensions {specs[i].width}x{specs[i].height}, expected {w}x{h}")
-        if summaries[i].n_positions == 0:
-            raise ValueError(f"game {i} has no positions")
-    lengths = np.array([summaries[i].n_positions for i in idx], dtype=np.int32)
-    rows = np.concatenate([pos_np[i, : summaries[i].n_positions] for i in idx])
+    sm = summ_np[idx]
+    lengths = sm["n_positions"].astype(np.int32)
+    if (lengths == 0).any():
+        raise ValueError(f"game {int(idx[np.argmin(lengths)])} has no positions")
+    block = pos_np[idx]
+    rows = block[np.arange(block.shape[1])[None, :] < lengths[:, None]]  # game-major, turn order inside a game
     sr = rows["search"]
     init = np.zeros((len(idx), h, w), dtype=np.bool_)
     for k, i in enumerate(idx):
-        for x, y in specs[i].cheese:
-            init[k, y, x] = True
-    outcomes = np.stack([
-        np.frombuffer(bytes(summaries[i].cheese_outcomes), dtype=np.uint8)[: h * w].astype(np.int8).reshape(h, w)
-        for i in idx])
+        c = np.asarray(specs[i].cheese, dtype=np.int64).reshape(-1, 2)
+        init[k, c[:, 1], c[:, 0]] = True
     return {
         "game_lengths": lengths,
-        "maze": np.stack([maze_array(specs[i]) for i in idx]).astype(np.int8),
+        "maze": np.stack([_maze_cached(specs[i]) for i in idx]),
         "initial_cheese": init,
-        "cheese_outcomes": outcomes,
+        "cheese_outcomes": sm["cheese_outcomes"][:, : h * w].astype(np.int8).reshape(len(idx), h, w),
         "max_turns": np.array([specs[i].max_turns for i in idx], dtype=np.int16),
-        "result": np.array([summaries[i].result for i in idx], dtype=np.int8),
-        "final_p1_score": np.array([summaries[i].final_p1_score for i in idx], dtype=np.float32),
-        "final_p2_score": np.array([summaries[i].final_p2_score for i in idx], dtype=np.float32),
+        "result": sm["result"].astype(np.int8),
+        "final_p1_score": sm["final_p1_score"].astype(np.float32),
+        "final_p2_score": sm["final_p2_score"].astype(np.float32),
         "p1_pos": np.stack([rows["p1_x"], rows["p1_y"]], axis=1).astype(np.int8),
         "p2_pos": np.stack([rows["p2_x"], rows["p2_y"]], axis=1).astype(np.int8),
         "p1_score": rows["p1_score"].astype(np.float32),
@@ -94,15 +118,29 @@ def write_bundle(path: Path, arrays: dict) -> None:
 
 
 def write_bundles(output_dir: Path, specs: Sequence[GameSpec], summaries, positions, stride: int,
-                  max_games_per_bundle: int = 32) -> list[Path]:
+                  max_games_per_bundle: int = 32, workers: int | None = None) -> list[Path]:
+    """One `bundle_{uuid}.npz` per `max_games_per_bundle` games.  Bundles are independent files, so they are
+    assembled and deflated on a small thread pool (zlib and the numpy copies release the GIL) — the reference
+    writes them on a dedicated writer thread while the games are played (recording.rs:174-230)."""
     output_dir.mkdir(parents=True, exist_ok=True)
     n = len(specs)
     pos_np = positions_as_numpy(positions, n, stride)
-    paths = []
     step = max(1, int(max_games_per_bundle))
-    for lo in range(0, n, step):
-        idx = list(range(lo, min(lo + step, n)))
-        path = output_dir / f"bundle_{uuid.uuid4()}.npz"
-        write_bundle(path, build_bundle_arrays(specs, summaries, pos_np, idx))
-        paths.append(path)
+    chunks = [list(range(lo, min(lo + step, n))) for lo in range(0, n, step)]
+    paths = [output_dir / f"bundle_{uuid.uuid4()}.npz" for _ in chunks]
+
+    summ_np = summaries_as_numpy(summaries, n)
+
+    def one(k: int) -> None:
+        write_bundle(paths[k], build_bundle_arrays(specs, summaries, pos_np, chunks[k], summ_np))
+
+    n_workers = min(len(chunks), workers if workers is not None else min(4, os.cpu_count() or 1))
+    if n_workers <= 1:
+        for k in range(len(chunks)):
+            one(k)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=n_workers) as pool:
+            list(pool.map(one, range(len(chunks))))  # re-raises the first failure
     return paths
