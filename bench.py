@@ -32,6 +32,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import queue
 import statistics
 import subprocess
 import sys
@@ -212,9 +213,29 @@ def run_cuda(args) -> None:
         return (step * world + rank) * n
 
     # ---- kernel-only: inputs resident, CUDA-event device time -----------------------------
-    batches = [make_batch(n, first_index(i)) for i in range(args.warmup + args.steps)]
+    # Batches are built by a feeder thread, two ahead of the step that plays them (building one takes about as
+    # long as playing it; the engine call releases the GIL, and the timed quantity is device time), so host memory
+    # and start-up time do not grow with --steps.
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    feed: queue.Queue = queue.Queue(maxsize=2)
+
+    def feeder() -> None:
+        try:
+            for i in range(args.warmup + args.steps):
+                feed.put(make_batch(n, first_index(i)))
+        except BaseException as exc:  # surfaces in the consumer instead of hanging it
+            feed.put(exc)
+
+    threading.Thread(target=feeder, daemon=True).start()
+
+    def next_batch():
+        b = feed.get()
+        if isinstance(b, BaseException):
+            raise b
+        return b
+
     for i in range(args.warmup):
-        eng.selfplay_upload(*batches[i])
+        eng.selfplay_upload(*next_batch())
         eng.selfplay_run_resident(cfg)
     sampler = ClockSampler(local)
     barrier()
@@ -222,8 +243,13 @@ def run_cuda(args) -> None:
         sampler.start()
     dev_ms = 0.0
     sims = sref = positions = path_nodes = new_nodes = launches = 0
+    kept = []  # the first timed batches are played again by the end-to-end leg
     for i in range(args.warmup, args.warmup + args.steps):
-        eng.selfplay_upload(*batches[i])
+        batch = next_batch()
+        if len(kept) < e2e_steps:
+            kept.append(batch)
+        eng.selfplay_upload(*batch)
+        del batch
         st = eng.selfplay_run_resident(cfg)
         dev_ms += st.device_ms
         path_nodes += st.path_nodes
@@ -240,9 +266,9 @@ def run_cuda(args) -> None:
     # ---- end to end through the public C-ABI call with host buffers -------------------------
     e2e_ms = 0.0
     e2e_sims = h2d = d2h = 0
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for i in range(e2e_steps):
-        pods, seeds = batches[args.warmup + i]
+    e2e_steps = min(e2e_steps, max(len(kept), 1))
+    for i in range(min(e2e_steps, len(kept))):
+        pods, seeds = kept[i]
         barrier()
         t0 = time.perf_counter()
         summ, pos, _, st = eng.selfplay(pods, cfg, seeds, stride=stride)
