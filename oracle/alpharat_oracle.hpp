@@ -24,7 +24,8 @@
 // What IS pinned: every golden vector / KAT the reference's own tests hold for this path
 // (tests/test_oracle_*.py, oracle/kat_tests.cpp): the 7 encoder fixtures, compute_outcomes
 // tables, smart_uniform_prior, calculate_collisions_left integers, backup / Welford KATs,
-// pruning cases, reward cases, accounting identities, xoshiro256++ reference vector.
+// pruning cases, reward cases, accounting identities, xoshiro256++ reference vector; the termination rule
+// against the reference's own Python statement of it (alpharat/eval/game.py:31-44).
 #pragma once
 #include <cstdint>
 #include <cstring>

@@ -149,3 +149,57 @@ def test_selfplay_stats_identities(oracle):
             assert r.nn_evals + r.terminals == 100
             total += r.total_visits
         assert total == s.total_simulations
+
+
+@pytest.mark.skipif(not Path("/root/reference/alpharat/eval/game.py").exists(),
+                    reason="the reference tree is only mounted in the build container")
+def test_termination_rule_matches_the_reference_python(oracle):
+    """`check_game_over` belongs to the third-party engine; the only statement of the rule inside the reference
+    is `is_terminal` (alpharat/eval/game.py:31-44: turn limit, no cheese left, strict majority of the total).  The
+    oracle's restatement is compared with that function itself (imported without the package __init__, which needs
+    the engine) on random states, half-point scores included."""
+    import importlib
+    import sys
+    import types
+
+    import numpy as np
+
+    from alpharat_b200.games import GameSpec, pods_array
+
+    saved = {k: sys.modules.get(k) for k in ("alpharat", "alpharat.eval", "alpharat.eval.game")}
+    try:
+        for name, path in (("alpharat", "/root/reference/alpharat"), ("alpharat.eval", "/root/reference/alpharat/eval")):
+            pkg = types.ModuleType(name)
+            pkg.__path__ = [path]
+            sys.modules[name] = pkg
+        is_terminal = importlib.import_module("alpharat.eval.game").is_terminal
+
+        class Fake:
+            def __init__(self, spec):
+                self.turn, self.max_turns = spec.turn, spec.max_turns
+                self.player1_score, self.player2_score = spec.p1_score, spec.p2_score
+                self._cheese = list(spec.cheese)
+
+            def cheese_positions(self):
+                return self._cheese
+
+        r = np.random.default_rng(7)
+        cells = [(x, y) for y in range(5) for x in range(5)]
+        specs = []
+        for _ in range(4000):
+            k = int(r.integers(0, 8))
+            cheese = [cells[i] for i in r.choice(25, size=k, replace=False)]
+            mt = int(r.integers(1, 40))
+            specs.append(GameSpec(5, 5, mt, (0, 0), (4, 4), cheese, turn=int(r.integers(0, mt + 3)),
+                                  p1_score=float(r.integers(0, 13)) / 2, p2_score=float(r.integers(0, 13)) / 2))
+        pods = pods_array(specs)
+        got = [bool(oracle.orc_game_over(C.byref(pods[i]))) for i in range(len(specs))]
+        want = [bool(is_terminal(Fake(s))) for s in specs]
+        assert got == want
+        assert 0.2 < sum(want) / len(want) < 0.95  # both outcomes are exercised
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
