@@ -343,6 +343,10 @@ def test_bundles_load_with_the_reference_loader(oracle, tmp_path):
             pkg.__path__ = [str(path)]
             sys.modules[name] = pkg
         loader = importlib.import_module("alpharat.data.loader")
+        ref_types = importlib.import_module("alpharat.data.types")
+        # the key names and outcome codes are the reference's own enums (alpharat/data/types.py:13-68)
+        assert {k.value for k in ref_types.GameFileKey} - {"num_positions"} == set(BUNDLE_KEYS)
+        assert [int(ref_types.CheeseOutcome[n]) for n in ("P1_WIN", "SIMULTANEOUS", "UNCOLLECTED", "P2_WIN")] == [0, 1, 2, 3]
 
         n = 5
         specs = (make_games(3, width=5, height=5, cheese_count=5, max_turns=30)
@@ -359,6 +363,11 @@ def test_bundles_load_with_the_reference_loader(oracle, tmp_path):
             assert (game.final_p1_score, game.final_p2_score) == (summ[g].final_p1_score, summ[g].final_p2_score)
             assert np.array_equal(game.maze, maze_array(specs[g]))
             assert sorted(map(tuple, np.argwhere(game.initial_cheese)[:, ::-1].tolist())) == sorted(specs[g].cheese)
+            codes = np.frombuffer(bytes(summ[g].cheese_outcomes), dtype=np.uint8)[:25].reshape(5, 5)
+            assert np.array_equal(np.asarray(game.cheese_outcomes), codes.astype(np.int8))
+            collected = {int(ref_types.CheeseOutcome.P1_WIN): 1.0, int(ref_types.CheeseOutcome.SIMULTANEOUS): 0.5}
+            p1_from_outcomes = sum(collected.get(int(c), 0.0) for c in codes[game.initial_cheese])
+            assert p1_from_outcomes == game.final_p1_score  # the attribution adds up to the score
             for t, p in enumerate(game.positions):
                 r = pos[g * stride + t]
                 assert (tuple(p.p1_pos), tuple(p.p2_pos)) == ((r.p1_x, r.p1_y), (r.p2_x, r.p2_y))
