@@ -484,3 +484,50 @@ def test_interface_surface_matches_the_reference_sources():
     st = SelfPlayStats(N.Stats())
     missing = [g for g in getters if not hasattr(st, g)]
     assert missing == [], missing
+
+
+@pytest.mark.skipif(not (REFERENCE / "alpharat" / "nn" / "extraction.py").exists(),
+                    reason="the reference tree is only mounted in the build container")
+def test_bundles_feed_the_reference_observation_builder(oracle, tmp_path):
+    """The training side of the drop-in (tests/data/test_rust_bundle_parity.py::test_observation_building): a
+    bundle written here, read back with the reference's loader, turned into `ObservationInput` by
+    `from_game_arrays` (alpharat/nn/extraction.py:15-44) and encoded by `FlatObservationBuilder`
+    (alpharat/nn/builders/flat.py:142-197) gives, position by position, the observation the encoder of the
+    self-play path (oracle `orc_encode`, pinned to the Rust fixtures) produces for the replayed game."""
+    import importlib
+    import sys
+    import types
+
+    names = ("alpharat", "alpharat.data", "alpharat.nn", "alpharat.nn.builders", "alpharat.nn.training")
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "alpharat" or k.startswith("alpharat.")}
+    try:
+        for name in names:
+            pkg = types.ModuleType(name)
+            pkg.__path__ = [str(REFERENCE / name.replace(".", "/"))]
+            sys.modules[name] = pkg
+        loader = importlib.import_module("alpharat.data.loader")
+        extraction = importlib.import_module("alpharat.nn.extraction")
+        flat = importlib.import_module("alpharat.nn.builders.flat")
+
+        specs = make_games(4, width=7, height=5, cheese_count=6, max_turns=25, maze_type="classic", first_index=3)
+        pods = pods_array(specs)
+        summ, pos, stride, st = oracle_selfplay(oracle, pods, search_cfg(simulations=40), [9, 8, 7, 6], n_threads=2)
+        path = write_bundles(tmp_path / "games", specs, summ, pos, stride, max_games_per_bundle=8)[0]
+        builder = flat.FlatObservationBuilder(width=7, height=5)
+        dim = 7 * 35 + 6
+        checked = 0
+        for g, game in enumerate(loader.load_game_bundle(path)):
+            replay = pods_array([specs[g]])
+            for t, position in enumerate(game.positions):
+                want = np.zeros(dim, dtype=np.float32)
+                oracle.orc_encode(replay, 1, want.ctypes.data_as(C.POINTER(C.c_float)))
+                got = np.asarray(builder.build(extraction.from_game_arrays(game, position)), dtype=np.float32)
+                assert got.shape == want.shape and np.abs(got - want).max() <= 1e-6, (g, t)
+                r = pos[g * stride + t]
+                oracle.orc_game_make_move(replay, r.action_p1, r.action_p2)
+                checked += 1
+        assert checked == st.total_positions > 20
+    finally:
+        for k in [k for k in sys.modules if k == "alpharat" or k.startswith("alpharat.")]:
+            del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
