@@ -84,3 +84,27 @@ def test_reference_format_checkpoints_load(tmp_path):
         assert rep["arch_ok"] and rep["all_tensors_passed"] and rep["f32_only"], (name, rep)
         assert rep["missing_or_misshaped"] == [], (name, rep["missing_or_misshaped"])
         assert rep["extra_in_reference"] == [], (name, rep["extra_in_reference"])
+
+
+@pytest.mark.skipif(not (REFERENCE / "alpharat" / "nn" / "models" / "mlp.py").exists(),
+                    reason="the reference tree is only mounted in the build container")
+def test_committed_goldens_are_what_the_reference_produces(tmp_path):
+    """`tests/golden/make_golden.py` is run again (the reference's FlatObservationBuilder, PyRatMLP, SymmetricMLP,
+    PyRatCNN and the Rust encoder fixtures) into a scratch directory; every committed golden file must hold the
+    same arrays.  A golden file edited by hand, or generated from anything but the reference, fails here."""
+    import numpy as np
+
+    gold = ROOT / "tests" / "golden"
+    r = subprocess.run([sys.executable, str(gold / "make_golden.py")], capture_output=True, text=True, timeout=900,
+                       env={**__import__("os").environ, "GOLDEN_OUT": str(tmp_path)})
+    assert r.returncode == 0, r.stderr[-3000:]
+    fresh = sorted(p.name for p in tmp_path.iterdir())
+    assert fresh == sorted(p.name for p in gold.iterdir() if p.suffix in (".npz", ".json"))
+    for name in fresh:
+        if name.endswith(".json"):
+            assert json.loads((tmp_path / name).read_text()) == json.loads((gold / name).read_text()), name
+            continue
+        a, b = np.load(tmp_path / name), np.load(gold / name)
+        assert sorted(a.files) == sorted(b.files), name
+        for k in a.files:
+            assert a[k].shape == b[k].shape and np.allclose(a[k], b[k], rtol=0, atol=2e-6), (name, k)
