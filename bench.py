@@ -109,6 +109,21 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+WORKLOAD_NAME = ("PyRat 7x7 open, 10 cheese, 50 turns, 7x7_rust_tuned (1897 sims, c_puct 0.512, "
+                 "fpu 0.459, force_k 0.103, batch 16), uniform priors, noise 0")
+
+
+def bench_config(args, world: int) -> dict:
+    """The `config` of the JSON line: identical for the CUDA arm and the reference arm."""
+    return {
+        "workload": WORKLOAD_NAME,
+        "concurrent_games_per_gpu": args.concurrent, "games_per_step_per_gpu": args.games_per_step,
+        "parallelism": f"games sharded over {world} GPU(s), no data-path collective",
+        "l2": "per-GPU node pools (GBs) exceed the 126 MB L2; fresh games every step",
+        "simulations_definition": "S_new = nn_evals + terminals (descents performed)",
+    }
+
+
 def make_batch(n: int, first_index: int):
     from alpharat_b200.games import make_games, pods_array
 
@@ -161,10 +176,10 @@ def run_reference(args) -> None:
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": busy / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "PyRat 7x7 open, 10 cheese, 50 turns, 7x7_rust_tuned (1897 sims, batch 16), "
-                               "uniform priors, noise 0; restated reference (C++ oracle) on host cores"},
+        "config": bench_config(args, args.gpus),
         "cpu_baseline": {"value": v, "unit": "simulations/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps of ~{args.ref_seconds:.0f} s each"},
+                         "sample": f"{args.steps} steps of ~{args.ref_seconds:.0f} s each of the same workload "
+                                   "(restated reference, C++ oracle, all host cores)"},
         "e2e": {"value": v, "unit": "simulations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -313,14 +328,7 @@ def run_cuda(args) -> None:
             "unit": "simulations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {
-                "workload": "PyRat 7x7 open, 10 cheese, 50 turns, 7x7_rust_tuned (1897 sims, c_puct 0.512, "
-                            "fpu 0.459, force_k 0.103, batch 16), uniform priors, noise 0",
-                "concurrent_games_per_gpu": args.concurrent, "games_per_step_per_gpu": n,
-                "parallelism": f"games sharded over {world} GPU(s), no data-path collective",
-                "l2": "per-GPU node pools (GBs) exceed the 126 MB L2; fresh games every step",
-                "simulations_definition": "S_new = nn_evals + terminals (descents performed)",
-            },
+            "config": bench_config(args, world),
             "games_per_hour": n * args.steps * world / (dev_ms * 1e-3) * 3600.0,
             "sref_per_s": sref / (dev_ms * 1e-3),
             "positions": positions,
