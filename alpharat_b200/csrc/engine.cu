@@ -14,8 +14,10 @@
 #include <thread>
 #include <vector>
 
+#include "host_tables.hpp"
 #include "mcts_device.cuh"
 #include "nn_api.cuh"
+#include "tree_thread.cuh"
 
 namespace ar {
 
@@ -293,6 +295,54 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(Ru
   }
 }
 
+
+
+// =========================================================================================
+// Uniform-prior self-play / search, thread-per-tree (tree_thread.cuh).  One persistent launch:
+// every thread claims games from an atomic counter (game_worker_loop, selfplay.rs:609-650) and
+// plays them to completion on device (play_game, selfplay.rs:515-598); SmartUniformBackend is
+// fused (priors written at node creation, leaf values 0).  The loop condition is warp-uniform so
+// that the 32 trees of a warp reconverge at every step.
+// =========================================================================================
+constexpr int TT_BLOCK = 32;
+__global__ void __launch_bounds__(TT_BLOCK) selfplay_tt_kernel(tt::Ctx c, int n_slots) {
+  extern __shared__ __align__(16) uint32_t tt_smem[];  // maze image: 16 words per tree, word-interleaved
+  const int slot = blockIdx.x * TT_BLOCK + threadIdx.x;
+  tt::TState s;
+  tt::TArr a;
+  tt::tt_init(s, c, (uint32_t)slot, tt_smem + threadIdx.x, TT_BLOCK);
+  if (slot >= n_slots) s.phase = tt::PH_EXIT;
+  const int lane = threadIdx.x & 31;
+  unsigned long long steps = 0;
+  // Warp-level phase scheduler: every iteration runs ONE phase, the one most of the warp's trees are in;
+  // the others wait (they cost nothing) and pile up until their phase is the majority.  This keeps the
+  // lanes converged: a descend step is ~8x the instructions of a backup step, so running both every
+  // iteration (plain divergence) left 5.7 of 32 lanes active (profiles/r2_tt_v2_divergent.md).
+  for (;;) {
+    const unsigned md = __ballot_sync(0xffffffffu, s.phase == tt::PH_DESCEND);
+    const unsigned mb = __ballot_sync(0xffffffffu, s.phase == tt::PH_BACKUP);
+    const unsigned mc = __ballot_sync(0xffffffffu, s.phase == tt::PH_CONTROL);
+    if (!(md | mb | mc)) break;
+    if (mc) {  // rare (a few per move) and it unblocks a tree: always first
+      const unsigned need = __ballot_sync(0xffffffffu, s.phase == tt::PH_CONTROL && s.cstate == tt::CS_COMPACT_MARK);
+      if (need) {
+        tt::coop_compact(s, c, need, lane);
+      } else if (s.phase == tt::PH_CONTROL) {
+        tt::control<true>(s, c);
+      }
+      continue;
+    }
+    if (__popc(mb) >= __popc(md)) {
+      if (s.phase == tt::PH_BACKUP) { tt::step_backup<true>(s, a, c); steps += 1; }
+    } else {
+      if (s.phase == tt::PH_DESCEND) { tt::step_descend<true>(s, a, c); steps += 1; }
+    }
+  }
+  atomicAdd(&c.counters[0], s.path_nodes);
+  atomicAdd(&c.counters[1], s.new_nodes);
+  atomicAdd(&c.counters[3], steps);
+  if (s.error) atomicCAS(c.error_flag, 0, (int)s.error);
+}
 
 // =========================================================================================
 // NN-guided mode: the search is cut at the evaluator.  One step = tree kernel (back up the
@@ -732,12 +782,18 @@ struct ar_engine {
   cudaStream_t stream2 = nullptr;              // second slot group of the NN-guided loop
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
-  // per-slot storage
+  // thread-per-tree uniform engine (tree_thread.cuh): paged node arena shared by all resident trees
+  uint8_t* tt_arena = nullptr;
+  uint32_t* tt_bitmap = nullptr;
+  uint32_t* tt_page_tables = nullptr;
+  uint32_t tt_n_pages = 0, tt_bitmap_words = 0, tt_pt_stride = 0, tt_slots = 0;
+  // per-slot storage of the warp-per-tree NN-guided engine (allocated on first use)
   NodeRec* pools = nullptr;
   uint32_t* path_bufs = nullptr;
   uint32_t* remaps = nullptr;
   uint16_t* coll_table = nullptr;
   uint32_t pool_nodes = 0, path_stride = 0, max_depth = 0, batch_cap = 0, n_slots = 0;
+  uint32_t node_cap = 0;  // nodes a tree may hold (pool_nodes of the engine cfg, or the worst case)
   ar_search_cfg coll_cfg{};
   uint32_t coll_len = 0;
   bool coll_valid = false;
@@ -754,6 +810,7 @@ struct ar_engine {
   size_t cap_dense = 0;
   int cap_offsets = 0;
   int n_resident = 0, resident_stride = 0;
+  bool last_run_nn = false;  // the NN-guided engine leaves cheese attribution to the download
   std::vector<ar_game_pod> h_games;  // kept for cheese-outcome attribution
   unsigned int* d_next = nullptr;
   unsigned long long* d_counters = nullptr;
@@ -795,33 +852,16 @@ static thread_local std::string g_create_error;
     }                                                                                     \
   } while (0)
 
-static uint32_t host_collisions_left(uint32_t n, const ar_search_cfg& c) {  // search.rs:437-450
-  if (n >= c.collision_scaling_end) return c.collision_limit_max;
-  if (n <= c.collision_scaling_start) return c.collision_limit_min;
-  float ratio = (float)(n - c.collision_scaling_start) /
-                (float)(c.collision_scaling_end - c.collision_scaling_start);
-  float scaled = (float)c.collision_limit_min +
-                 ((float)c.collision_limit_max - (float)c.collision_limit_min) *
-                     powf(ratio, c.collision_scaling_power);
-  float r = roundf(scaled);
-  uint32_t v = !(r > 0.0f) ? 0u : (r >= 4294967296.0f ? 0xffffffffu : (uint32_t)r);
-  return std::min(std::max(v, c.collision_limit_min), c.collision_limit_max);
-}
-
 static ar_status ensure_coll_table(ar_engine* e, const ar_search_cfg& c) {
   if (e->coll_valid && memcmp(&e->coll_cfg.collision_limit_min, &c.collision_limit_min,
                               sizeof(uint32_t) * 4 + sizeof(float)) == 0)
     return AR_OK;
   // beyond collision_scaling_end the budget is constant, so the table may be clamped
-  if (c.collision_scaling_end >= e->coll_len && e->pool_nodes + 1 > e->coll_len) {
+  if (c.collision_scaling_end >= e->coll_len && e->node_cap + 1 > e->coll_len) {
     e->err = "collision_scaling_end beyond the collision table";
     return AR_ERR_UNSUPPORTED;
   }
-  std::vector<uint16_t> t(e->coll_len);
-  for (uint32_t n = 0; n < e->coll_len; ++n) {
-    uint32_t v = host_collisions_left(n, c);
-    t[n] = (uint16_t)std::min<uint32_t>(v, 65535u);
-  }
+  std::vector<uint16_t> t = ar_host::collision_table(c, e->coll_len);
   CK(cudaMemcpyAsync(e->coll_table, t.data(), t.size() * sizeof(uint16_t), cudaMemcpyHostToDevice,
                      e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -936,21 +976,19 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
   if (ce != cudaSuccess) return fail(AR_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
   e->device = cfg->device;
   e->n_slots = cfg->concurrent_games;
-  // Pool sizing: a tree can keep growing through tree reuse, by at most `simulations` nodes per
-  // move, so max_turns * max_simulations + 2 nodes can never overflow.  Use that when it fits in
-  // 70 % of free HBM, otherwise the largest pool that does (overflow is then a loud error).
-  uint64_t pn = cfg->pool_nodes;
-  if (pn == 0) {
-    size_t free_b = 0, total_b = 0;
-    cudaError_t me = cudaMemGetInfo(&free_b, &total_b);
-    if (me != cudaSuccess) return fail(AR_ERR_CUDA, std::string("cudaMemGetInfo: ") + cudaGetErrorString(me));
-    uint64_t worst = (uint64_t)cfg->max_turns * std::max<uint32_t>(cfg->max_simulations, 1) + 2;
-    uint64_t fit = (uint64_t)(0.70 * (double)free_b) / cfg->concurrent_games / (sizeof(NodeRec) + sizeof(uint32_t));
-    pn = std::max<uint64_t>(std::min(worst, fit), 64);
+  // Node capacity per tree: a tree can keep growing through tree reuse, by at most `simulations`
+  // nodes per move, so max_turns * max_simulations + 2 nodes can never overflow.  The thread-per-tree
+  // engine pages its pools (capacity = page-table length, memory is committed as trees grow); the
+  // NN-guided engine sizes fixed pools when it is first used (ensure_nn_pools).
+  {
+    const uint64_t worst = (uint64_t)cfg->max_turns * std::max<uint32_t>(cfg->max_simulations, 1) + 2;
+    uint64_t cap = cfg->pool_nodes ? cfg->pool_nodes : worst;
+    cap = std::min<uint64_t>(cap, (1ull << PATH_NODE_BITS) - 1);
+    if (cap < 64) return fail(AR_ERR_INVALID_ARG, "pool_nodes must be >= 64");
+    e->node_cap = (uint32_t)cap;
+    e->tt_pt_stride = (uint32_t)((cap + tt::PAGE_NODES - 1) / tt::PAGE_NODES);
+    e->tt_slots = (cfg->concurrent_games + TT_BLOCK - 1) / TT_BLOCK * TT_BLOCK;
   }
-  pn = std::min<uint64_t>(pn, (1ull << PATH_NODE_BITS) - 1);
-  if (pn < 64) return fail(AR_ERR_INVALID_ARG, "pool_nodes must be >= 64");
-  e->pool_nodes = (uint32_t)pn;
   e->max_depth = cfg->max_turns + 1;
   e->path_stride = e->max_depth + 1;
   e->batch_cap = cfg->max_batch_size;
@@ -967,17 +1005,13 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
   CKC(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   CKC(cudaEventCreate(&e->ev0));
   CKC(cudaEventCreate(&e->ev1));
-  CKC(cudaMalloc(&e->pools, (size_t)e->n_slots * (size_t)pn * sizeof(NodeRec)));
-  CKC(cudaMalloc(&e->path_bufs, (size_t)e->n_slots * e->batch_cap * e->path_stride * sizeof(uint32_t)));
-  CKC(cudaMalloc(&e->remaps, (size_t)e->n_slots * pn * sizeof(uint32_t)));
-  e->coll_len = (uint32_t)std::min<uint64_t>(pn + 1, 1u << 20);
+  e->coll_len = (uint32_t)std::min<uint64_t>((uint64_t)e->node_cap + 2, 1u << 20);
   CKC(cudaMalloc(&e->coll_table, (size_t)e->coll_len * sizeof(uint16_t)));
   CKC(cudaMalloc(&e->d_next, sizeof(unsigned int)));
   CKC(cudaMalloc(&e->d_counters, 8 * sizeof(unsigned long long)));
   CKC(cudaMalloc(&e->d_error, sizeof(int)));
   CKC(cudaHostAlloc(&e->h_progress, sizeof(ar_progress), cudaHostAllocMapped));
   CKC(cudaHostGetDevicePointer(&e->d_progress, e->h_progress, 0));
-  CKC(cudaFuncSetAttribute(selfplay_uniform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CKC(cudaFuncSetAttribute(nn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #undef CKC
   *out = e;
@@ -988,6 +1022,7 @@ void ar_engine_destroy(ar_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaFree(e->pools); cudaFree(e->path_bufs); cudaFree(e->remaps); cudaFree(e->coll_table);
+  cudaFree(e->tt_arena); cudaFree(e->tt_bitmap); cudaFree(e->tt_page_tables);
   cudaFree(e->d_games); cudaFree(e->d_seeds); cudaFree(e->d_summaries); cudaFree(e->d_positions);
   cudaFree(e->d_search); cudaFree(e->d_next); cudaFree(e->d_counters); cudaFree(e->d_error);
   cudaFree(e->d_rows); cudaFree(e->d_nn_out);
@@ -1046,6 +1081,58 @@ ar_status ar_engine_set_eval_cache(ar_engine* e, uint32_t entries_per_tree) {
   while (n > 64 && (size_t)n * e->n_slots * sizeof(CacheEnt) > ((size_t)8 << 30)) n >>= 1;
   CK(cudaMalloc(&e->d_cache, (size_t)n * e->n_slots * sizeof(CacheEnt)));
   e->cache_entries = n;
+  return AR_OK;
+}
+
+
+static void free_tt(ar_engine* e) {
+  cudaFree(e->tt_arena); cudaFree(e->tt_bitmap); cudaFree(e->tt_page_tables);
+  e->tt_arena = nullptr; e->tt_bitmap = nullptr; e->tt_page_tables = nullptr;
+  e->tt_n_pages = 0;
+}
+static void free_nn_pools(ar_engine* e) {
+  cudaFree(e->pools); cudaFree(e->path_bufs); cudaFree(e->remaps);
+  e->pools = nullptr; e->path_bufs = nullptr; e->remaps = nullptr;
+  e->pool_nodes = 0;
+}
+
+// Paged arena of the thread-per-tree engine: every resident tree owns page `slot` for good, the rest
+// is handed out on demand.  Sized for the worst case when that fits in 70 % of free HBM (it never
+// does for production configurations: 32768 trees x 93 pages), otherwise everything that fits.
+static ar_status ensure_tt(ar_engine* e) {
+  if (e->tt_arena) return AR_OK;
+  free_nn_pools(e);
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const uint64_t worst = (uint64_t)e->tt_slots * e->tt_pt_stride + 8;
+  const uint64_t fit = (uint64_t)(0.70 * (double)free_b) / tt::PAGE_BYTES;
+  const uint64_t pages = std::min(worst, fit);
+  if (pages < (uint64_t)e->tt_slots + 4) {
+    e->err = "not enough free device memory for " + std::to_string(e->tt_slots) + " resident trees";
+    return AR_ERR_CUDA;
+  }
+  e->tt_n_pages = (uint32_t)pages;
+  e->tt_bitmap_words = (e->tt_n_pages + 31) / 32;
+  CK(cudaMalloc(&e->tt_arena, (size_t)pages * tt::PAGE_BYTES));
+  CK(cudaMalloc(&e->tt_bitmap, (size_t)e->tt_bitmap_words * sizeof(uint32_t)));
+  CK(cudaMalloc(&e->tt_page_tables, (size_t)e->tt_slots * e->tt_pt_stride * sizeof(uint32_t)));
+  CK(cudaFuncSetAttribute(selfplay_tt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_BLOCK * 64));
+  return AR_OK;
+}
+
+// Fixed pools of the warp-per-tree NN-guided engine.
+static ar_status ensure_nn_pools(ar_engine* e) {
+  if (e->pools) return AR_OK;
+  free_tt(e);
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const uint64_t fit = (uint64_t)(0.70 * (double)free_b) / e->n_slots / (sizeof(NodeRec) + sizeof(uint32_t));
+  uint64_t pn = e->cfg.pool_nodes ? e->cfg.pool_nodes : std::max<uint64_t>(std::min<uint64_t>(e->node_cap, fit), 64);
+  pn = std::min<uint64_t>(pn, (1ull << PATH_NODE_BITS) - 1);
+  e->pool_nodes = (uint32_t)pn;
+  CK(cudaMalloc(&e->pools, (size_t)e->n_slots * (size_t)pn * sizeof(NodeRec)));
+  CK(cudaMalloc(&e->path_bufs, (size_t)e->n_slots * e->batch_cap * e->path_stride * sizeof(uint32_t)));
+  CK(cudaMalloc(&e->remaps, (size_t)e->n_slots * pn * sizeof(uint32_t)));
   return AR_OK;
 }
 
@@ -1108,17 +1195,47 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
   size_t smem = 4 * warp_smem_bytes(e->max_depth, e->batch_cap);
   int slots = std::min<int>(e->n_slots, std::max(p.n_games, 1));
   p.n_slots = slots;
-  int blocks = (slots + 3) / 4;
   const bool nn = e->arch != AR_ARCH_UNIFORM;
+  e->last_run_nn = nn;
+  if (!nn) {
+    ar_status s = ensure_tt(e);
+    if (s) return s;
+    // every launch starts with only the trees' own first pages taken: bits [0, tt_slots)
+    CK(cudaMemsetAsync(e->tt_bitmap, 0, (size_t)e->tt_bitmap_words * sizeof(uint32_t), e->stream));
+    CK(cudaMemsetAsync(e->tt_bitmap, 0xff, (size_t)e->tt_slots / 8, e->stream));
+  }
   if (nn) {
-    ar_status s = ensure_nn_buffers(e);
+    ar_status s = ensure_nn_pools(e);
+    if (s) return s;
+    p.pools = e->pools; p.pool_nodes = e->pool_nodes; p.path_bufs = e->path_bufs; p.remaps = e->remaps;
+    s = ensure_nn_buffers(e);
     if (s) return s;
     s = ensure_maze_table(e, p.n_games);
     if (s) return s;
   }
   CK(cudaEventRecord(e->ev0, e->stream));
   if (!nn) {
-    selfplay_uniform_kernel<<<blocks, 128, smem, e->stream>>>(p);
+    tt::Ctx c{};
+    c.arena = e->tt_arena;
+    c.page_bitmap = e->tt_bitmap;
+    c.n_pages = e->tt_n_pages;
+    c.bitmap_words = e->tt_bitmap_words;
+    c.page_tables = e->tt_page_tables;
+    c.pt_stride = e->tt_pt_stride;
+    c.coll_table = e->coll_table;
+    c.coll_len = e->coll_len;
+    c.sp.c_puct = p.sp.c_puct; c.sp.fpu_reduction = p.sp.fpu_reduction; c.sp.force_k = p.sp.force_k;
+    c.sp.noise_epsilon = p.sp.noise_epsilon; c.sp.noise_concentration = p.sp.noise_concentration;
+    c.sp.n_sims = p.sp.n_sims; c.sp.batch_size = p.sp.batch_size;
+    c.games = p.games; c.seeds = p.seeds; c.n_games = p.n_games;
+    c.next_game = e->d_next;
+    c.summaries = p.summaries; c.positions = p.positions; c.pos_stride = p.pos_stride;
+    c.search_out = p.search_out; c.search_only = p.search_only;
+    c.counters = e->d_counters;
+    c.error_flag = e->d_error;
+    c.progress = p.progress;
+    const int tslots = (std::min<int>((int)e->tt_slots, std::max(p.n_games, 1)) + TT_BLOCK - 1) / TT_BLOCK * TT_BLOCK;
+    selfplay_tt_kernel<<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->stream>>>(c, tslots);
     CK(cudaGetLastError());
     e->launches += 1;
   } else {
@@ -1254,7 +1371,7 @@ ar_status ar_search_batch(ar_engine* e, const ar_game_pod* games, int32_t n, con
   if (s) return s;
   if (n == 0) return AR_OK;
   if (!seeds || !out) { e->err = "seeds/out is NULL"; return AR_ERR_INVALID_ARG; }
-  if ((uint64_t)cfg->simulations + 2 > e->pool_nodes) { e->err = "simulations exceed pool_nodes"; return AR_ERR_POOL_OVERFLOW; }
+  if ((uint64_t)cfg->simulations + 2 > e->node_cap) { e->err = "simulations exceed pool_nodes"; return AR_ERR_POOL_OVERFLOW; }
   if (e->arch != AR_ARCH_UNIFORM)
     for (int i = 0; i < n; ++i)
       if (games[i].width != e->nn_width || games[i].height != e->nn_height) {
@@ -1447,7 +1564,7 @@ ar_status ar_selfplay_download(ar_engine* e, ar_game_summary* summaries, ar_posi
       ar_position_record* dst = positions + (size_t)i * positions_stride;
       if (summaries[i].n_positions)
         memcpy(dst, e->h_dense + off[i], (size_t)summaries[i].n_positions * sizeof(ar_position_record));
-      attribute_cheese(e->h_games[i], summaries[i], dst);
+      if (e->last_run_nn) attribute_cheese(e->h_games[i], summaries[i], dst);
     }
   };
   const int n_thr = n >= 4096 ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;

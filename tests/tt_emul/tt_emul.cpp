@@ -53,6 +53,7 @@ extern "C" int tt_emul_run(const ar_game_pod* games, int n, const ar_search_cfg*
 
   std::vector<uint32_t> maze((size_t)16 * n_threads, 0);
   std::vector<TState> st(n_threads);
+  std::vector<TArr> arr(n_threads);
   for (int t = 0; t < n_threads; ++t) tt_init(st[t], c, (uint32_t)t, maze.data() + t, n_threads);
   unsigned long long steps = 0, peak = 0;
   for (;;) {
@@ -60,7 +61,7 @@ extern "C" int tt_emul_run(const ar_game_pod* games, int n, const ar_search_cfg*
     for (int t = 0; t < n_threads; ++t) {
       if (st[t].phase == PH_EXIT) continue;
       alive += 1;
-      tt_step<false>(st[t], c);
+      tt_step<false>(st[t], arr[t], c);
       steps += 1;
     }
     if ((steps & 0xfff) < (unsigned)n_threads) {
