@@ -11,7 +11,8 @@ import ctypes as C
 import os
 from pathlib import Path
 
-AR_ABI_VERSION = 1
+AR_ABI_VERSION = 2
+AR_TREE_WARP, AR_TREE_THREAD = 0, 1
 AR_MAX_CELLS = 256
 
 AR_OK = 0
@@ -122,6 +123,7 @@ class EngineCfg(C.Structure):
         ("concurrent_games", C.c_uint32), ("pool_nodes", C.c_uint32),
         ("max_cells", C.c_uint32), ("max_turns", C.c_uint32),
         ("max_batch_size", C.c_uint32), ("max_simulations", C.c_uint32),
+        ("tree_engine", C.c_uint32),
     ]
 
 

@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -195,6 +196,7 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(Ru
     const int cheese_available = __popcll(g.cheese);
     cx.epoch += 1;
     init_root(cx, g, lane);
+    if (!p.search_only) init_cheese_outcomes(p.summaries[gi], lane);
 
     uint32_t n_pos = 0;
     unsigned long long tot_sims = 0, tot_nn = 0, tot_term = 0, tot_coll = 0;
@@ -244,8 +246,10 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(Ru
       uint32_t rmeta = cx.pool[0].s[LANE_LINKS].y;
       int i = action_to_idx(meta_m1(rmeta), a1), j = action_to_idx(meta_m2(rmeta), a2);
       uint32_t child = reinterpret_cast<const uint32_t*>(&cx.pool[0].s[LANE_CHILD])[i * 5 + j];
+      const uint64_t cheese_before = g.cheese;
       game_step(g, i, j, cx.steptbl());  // the table is indexed by outcome (blocked move = STAY's outcome)
       turn += 1;
+      if (lane == 0) credit_cheese(p.summaries[gi], cheese_before, g);
       __syncwarp();
       AR_T0();
       if (game_over(g, turn, cx.max_turns)) break;  // the tree of a finished game is dropped
@@ -271,9 +275,8 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(Ru
       s.total_nn_evals = tot_nn;
       s.total_terminals = tot_term;
       s.total_collisions = tot_coll;
-      // final state, consumed by the host-side cheese-outcome attribution
-      s.reserved[0] = (uint8_t)g.p1; s.reserved[1] = (uint8_t)g.p2; s.reserved[2] = 0;
-      *reinterpret_cast<uint64_t*>(s.cheese_outcomes) = g.cheese;
+      s.reserved[0] = s.reserved[1] = s.reserved[2] = 0;
+      s.reserved1 = 0;
       if (p.progress) {
         atomicAdd_system((unsigned long long*)&p.progress->positions_completed, (unsigned long long)n_pos);
         atomicAdd_system((unsigned long long*)&p.progress->simulations_completed, tot_sims);
@@ -305,7 +308,8 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(Ru
 // that the 32 trees of a warp reconverge at every step.
 // =========================================================================================
 constexpr int TT_BLOCK = 32;
-__global__ void __launch_bounds__(TT_BLOCK) selfplay_tt_kernel(tt::Ctx c, int n_slots) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(TT_BLOCK, MIN_BLOCKS) selfplay_tt_kernel(tt::Ctx c, int n_slots) {
   extern __shared__ __align__(16) uint32_t tt_smem[];  // maze image: 16 words per tree, word-interleaved
   const int slot = blockIdx.x * TT_BLOCK + threadIdx.x;
   tt::TState s;
@@ -342,6 +346,91 @@ __global__ void __launch_bounds__(TT_BLOCK) selfplay_tt_kernel(tt::Ctx c, int n_
   atomicAdd(&c.counters[1], s.new_nodes);
   atomicAdd(&c.counters[3], steps);
   if (s.error) atomicCAS(c.error_flag, 0, (int)s.error);
+}
+
+
+// Block-sorted variant: the trees' state lives in shared memory instead of registers, and every
+// iteration the block sorts its trees by phase, so a warp runs 32 trees that are all in the SAME phase
+// (descend / backup / control) — only the warps at a phase boundary diverge.  Registers are bound to
+// work items for one step only; a tree is picked up by whichever lane its rank in the sorted order says.
+// (With trees bound to lanes 7.7 of 32 lanes were active on the real workload, profiles/r2_tt_lanes.md.)
+constexpr int TB_BLOCK = 128;
+constexpr int TB_BACKUP_NODES = 4;
+__host__ __device__ inline size_t tb_smem_bytes() { return (size_t)TB_BLOCK * (sizeof(tt::TState) + 64 + 2 + 2) + 256; }
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(TB_BLOCK, MIN_BLOCKS) selfplay_tb_kernel(tt::Ctx c, tt::TArr* arrs) {
+  extern __shared__ __align__(16) uint8_t tb_smem[];
+  tt::TState* st = reinterpret_cast<tt::TState*>(tb_smem);
+  uint32_t* maze = reinterpret_cast<uint32_t*>(st + TB_BLOCK);              // [16][TB_BLOCK]
+  uint16_t* order = reinterpret_cast<uint16_t*>(maze + 16 * TB_BLOCK);      // trees sorted by phase
+  uint16_t* creq = order + TB_BLOCK;                                        // trees that asked for a compaction
+  int* wcnt = reinterpret_cast<int*>(creq + TB_BLOCK);                      // [4 classes][4 warps] + totals
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NW = TB_BLOCK / 32;
+  {
+    tt::TState s;
+    tt::tt_init(s, c, (uint32_t)(blockIdx.x * TB_BLOCK + tid), maze + tid, TB_BLOCK);
+    st[tid] = s;
+  }
+  tt::TArr* my_arrs = arrs + (size_t)blockIdx.x * TB_BLOCK;
+  unsigned long long steps = 0;
+  __syncthreads();
+  for (;;) {
+    // ---- classify this thread's own tree: 0 descend, 1 backup, 2 control, 3 compaction request, 4 exited
+    const int ph = st[tid].phase;
+    int cls = ph == tt::PH_DESCEND ? 0 : ph == tt::PH_BACKUP ? 1 : ph == tt::PH_CONTROL ? 2 : 4;
+    if (cls == 2 && st[tid].cstate == tt::CS_COMPACT_MARK) cls = 3;
+    unsigned bal[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bal[k] = __ballot_sync(0xffffffffu, cls == k);
+    if (lane < 4) wcnt[lane * NW + wid] = __popc(bal[lane]);
+    __syncthreads();
+    // ---- ranks: class-major, then warp, then lane
+    int base[4], total = 0, n_creq = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int before = 0, all = 0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const int v = wcnt[k * NW + w];
+        before += w < wid ? v : 0;
+        all += v;
+      }
+      if (k < 3) { base[k] = total + before; total += all; } else { base[k] = before; n_creq = all; }
+    }
+    if (total == 0 && n_creq == 0) break;
+    if (cls < 3) order[base[cls] + __popc(bal[cls] & ((1u << lane) - 1u))] = (uint16_t)tid;
+    else if (cls == 3) creq[base[3] + __popc(bal[3] & ((1u << lane) - 1u))] = (uint16_t)tid;
+    __syncthreads();
+    // ---- compaction requests: one warp per tree, all 32 lanes (tree_thread.cuh coop_compact_tree)
+    for (int r = wid; r < n_creq; r += NW) {
+      tt::TState& ts = st[creq[r]];
+      const uint32_t kept = tt::coop_compact_tree(ts.pt, c.arena, ts.cp_count, ts.cp_new_root, ts.cp_page0, ts.cp_page1,
+                                                  ts.cp_page2, ts.cp_page3, lane);
+      if (lane == 0) {
+        ts.cp_kept = kept;
+        tt::compact_end(ts, c);
+        ts.cstate = tt::CS_MOVE_START;
+      }
+      __syncwarp();
+    }
+    // ---- one step for the tree of this thread's rank
+    if (tid < total) {
+      const int tree = order[tid];
+      tt::TState s = st[tree];
+      tt::TArr& a = my_arrs[tree];
+      if (s.phase == tt::PH_DESCEND) tt::step_descend<true>(s, a, c);
+      else if (s.phase == tt::PH_BACKUP) tt::step_backup<true>(s, a, c, TB_BACKUP_NODES);
+      else tt::control<true>(s, c);
+      st[tree] = s;
+      steps += 1;
+    }
+    __syncthreads();
+  }
+  atomicAdd(&c.counters[0], st[tid].path_nodes);
+  atomicAdd(&c.counters[1], st[tid].new_nodes);
+  atomicAdd(&c.counters[3], steps);
+  if (st[tid].error) atomicCAS(c.error_flag, 0, (int)st[tid].error);
 }
 
 // =========================================================================================
@@ -541,6 +630,7 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
       st.cheese_available = __popcll(g.cheese);
       cx.epoch += 1;
       init_root(cx, g, lane);
+      if (!p.search_only) init_cheese_outcomes(p.summaries[gi], lane);
       st.n_pos = 0;
       st.tot_sims = st.tot_nn = st.tot_term = st.tot_coll = 0;
       st.remaining = sp.n_sims;
@@ -597,8 +687,10 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
           uint32_t rmeta = cx.pool[0].s[LANE_LINKS].y;
           int i = action_to_idx(meta_m1(rmeta), a1), j = action_to_idx(meta_m2(rmeta), a2);
           uint32_t child = reinterpret_cast<const uint32_t*>(&cx.pool[0].s[LANE_CHILD])[i * 5 + j];
+          const uint64_t cheese_before = g.cheese;
           game_step(g, i, j, cx.steptbl());  // indexed by outcome
           turn += 1;
+          if (lane == 0) credit_cheese(p.summaries[st.gi], cheese_before, g);
           __syncwarp();
           moved = true;
           if (!game_over(g, turn, cx.max_turns)) {  // the tree of a finished game is dropped
@@ -624,8 +716,8 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p
             s.total_nn_evals = st.tot_nn;
             s.total_terminals = st.tot_term;
             s.total_collisions = st.tot_coll;
-            s.reserved[0] = (uint8_t)g.p1; s.reserved[1] = (uint8_t)g.p2; s.reserved[2] = 0;
-            *reinterpret_cast<uint64_t*>(s.cheese_outcomes) = g.cheese;
+            s.reserved[0] = s.reserved[1] = s.reserved[2] = 0;
+            s.reserved1 = 0;
             if (p.progress) {
               atomicAdd_system((unsigned long long*)&p.progress->positions_completed, (unsigned long long)st.n_pos);
               atomicAdd_system((unsigned long long*)&p.progress->simulations_completed, st.tot_sims);
@@ -787,6 +879,7 @@ struct ar_engine {
   uint32_t* tt_bitmap = nullptr;
   uint32_t* tt_page_tables = nullptr;
   uint32_t tt_n_pages = 0, tt_bitmap_words = 0, tt_pt_stride = 0, tt_slots = 0;
+  tt::TArr* tt_arrs = nullptr;  // per-tree cell stack + batch entries of the block-sorted kernel
   // per-slot storage of the warp-per-tree NN-guided engine (allocated on first use)
   NodeRec* pools = nullptr;
   uint32_t* path_bufs = nullptr;
@@ -810,7 +903,6 @@ struct ar_engine {
   size_t cap_dense = 0;
   int cap_offsets = 0;
   int n_resident = 0, resident_stride = 0;
-  bool last_run_nn = false;  // the NN-guided engine leaves cheese attribution to the download
   std::vector<ar_game_pod> h_games;  // kept for cheese-outcome attribution
   unsigned int* d_next = nullptr;
   unsigned long long* d_counters = nullptr;
@@ -969,6 +1061,7 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
     return s;
   };
   if (cfg->concurrent_games == 0) return fail(AR_ERR_INVALID_ARG, "concurrent_games must be > 0");
+  if (cfg->tree_engine > AR_TREE_THREAD) return fail(AR_ERR_INVALID_ARG, "tree_engine must be AR_TREE_WARP or AR_TREE_THREAD");
   if (cfg->max_cells == 0 || cfg->max_cells > 64) return fail(AR_ERR_UNSUPPORTED, "max_cells must be in [1, 64] in this build");
   if (cfg->max_batch_size == 0 || cfg->max_batch_size > MAX_BATCH) return fail(AR_ERR_INVALID_ARG, "max_batch_size must be in [1, 64]");
   if (cfg->max_turns == 0 || cfg->max_turns > 250) return fail(AR_ERR_UNSUPPORTED, "max_turns must be in [1, 250] in this build (8-bit path depth)");
@@ -987,7 +1080,7 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
     if (cap < 64) return fail(AR_ERR_INVALID_ARG, "pool_nodes must be >= 64");
     e->node_cap = (uint32_t)cap;
     e->tt_pt_stride = (uint32_t)((cap + tt::PAGE_NODES - 1) / tt::PAGE_NODES);
-    e->tt_slots = (cfg->concurrent_games + TT_BLOCK - 1) / TT_BLOCK * TT_BLOCK;
+    e->tt_slots = (cfg->concurrent_games + TB_BLOCK - 1) / TB_BLOCK * TB_BLOCK;
   }
   e->max_depth = cfg->max_turns + 1;
   e->path_stride = e->max_depth + 1;
@@ -1012,6 +1105,7 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
   CKC(cudaMalloc(&e->d_error, sizeof(int)));
   CKC(cudaHostAlloc(&e->h_progress, sizeof(ar_progress), cudaHostAllocMapped));
   CKC(cudaHostGetDevicePointer(&e->d_progress, e->h_progress, 0));
+  CKC(cudaFuncSetAttribute(selfplay_uniform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CKC(cudaFuncSetAttribute(nn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #undef CKC
   *out = e;
@@ -1022,7 +1116,7 @@ void ar_engine_destroy(ar_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaFree(e->pools); cudaFree(e->path_bufs); cudaFree(e->remaps); cudaFree(e->coll_table);
-  cudaFree(e->tt_arena); cudaFree(e->tt_bitmap); cudaFree(e->tt_page_tables);
+  cudaFree(e->tt_arena); cudaFree(e->tt_bitmap); cudaFree(e->tt_page_tables); cudaFree(e->tt_arrs);
   cudaFree(e->d_games); cudaFree(e->d_seeds); cudaFree(e->d_summaries); cudaFree(e->d_positions);
   cudaFree(e->d_search); cudaFree(e->d_next); cudaFree(e->d_counters); cudaFree(e->d_error);
   cudaFree(e->d_rows); cudaFree(e->d_nn_out);
@@ -1086,8 +1180,8 @@ ar_status ar_engine_set_eval_cache(ar_engine* e, uint32_t entries_per_tree) {
 
 
 static void free_tt(ar_engine* e) {
-  cudaFree(e->tt_arena); cudaFree(e->tt_bitmap); cudaFree(e->tt_page_tables);
-  e->tt_arena = nullptr; e->tt_bitmap = nullptr; e->tt_page_tables = nullptr;
+  cudaFree(e->tt_arena); cudaFree(e->tt_bitmap); cudaFree(e->tt_page_tables); cudaFree(e->tt_arrs);
+  e->tt_arena = nullptr; e->tt_bitmap = nullptr; e->tt_page_tables = nullptr; e->tt_arrs = nullptr;
   e->tt_n_pages = 0;
 }
 static void free_nn_pools(ar_engine* e) {
@@ -1105,7 +1199,9 @@ static ar_status ensure_tt(ar_engine* e) {
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
   const uint64_t worst = (uint64_t)e->tt_slots * e->tt_pt_stride + 8;
-  const uint64_t fit = (uint64_t)(0.70 * (double)free_b) / tt::PAGE_BYTES;
+  uint64_t fit = (uint64_t)(0.70 * (double)free_b) / tt::PAGE_BYTES;
+  if (const char* v = getenv("AR_TT_ARENA_GB"))  // profiling knob: a small arena keeps ncu's save / restore of device memory cheap
+    fit = std::min<uint64_t>(fit, (uint64_t)(atof(v) * 1e9) / tt::PAGE_BYTES);
   const uint64_t pages = std::min(worst, fit);
   if (pages < (uint64_t)e->tt_slots + 4) {
     e->err = "not enough free device memory for " + std::to_string(e->tt_slots) + " resident trees";
@@ -1116,7 +1212,9 @@ static ar_status ensure_tt(ar_engine* e) {
   CK(cudaMalloc(&e->tt_arena, (size_t)pages * tt::PAGE_BYTES));
   CK(cudaMalloc(&e->tt_bitmap, (size_t)e->tt_bitmap_words * sizeof(uint32_t)));
   CK(cudaMalloc(&e->tt_page_tables, (size_t)e->tt_slots * e->tt_pt_stride * sizeof(uint32_t)));
-  CK(cudaFuncSetAttribute(selfplay_tt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_BLOCK * 64));
+  CK(cudaMalloc(&e->tt_arrs, (size_t)e->tt_slots * sizeof(tt::TArr)));
+  CK(cudaFuncSetAttribute(selfplay_tb_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem_bytes()));
+  CK(cudaFuncSetAttribute(selfplay_tb_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem_bytes()));
   return AR_OK;
 }
 
@@ -1196,25 +1294,31 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
   int slots = std::min<int>(e->n_slots, std::max(p.n_games, 1));
   p.n_slots = slots;
   const bool nn = e->arch != AR_ARCH_UNIFORM;
-  e->last_run_nn = nn;
-  if (!nn) {
+  const bool tt_run = !nn && e->cfg.tree_engine == AR_TREE_THREAD;
+  if (tt_run) {
     ar_status s = ensure_tt(e);
     if (s) return s;
     // every launch starts with only the trees' own first pages taken: bits [0, tt_slots)
     CK(cudaMemsetAsync(e->tt_bitmap, 0, (size_t)e->tt_bitmap_words * sizeof(uint32_t), e->stream));
     CK(cudaMemsetAsync(e->tt_bitmap, 0xff, (size_t)e->tt_slots / 8, e->stream));
   }
-  if (nn) {
+  if (!tt_run) {
     ar_status s = ensure_nn_pools(e);
     if (s) return s;
     p.pools = e->pools; p.pool_nodes = e->pool_nodes; p.path_bufs = e->path_bufs; p.remaps = e->remaps;
-    s = ensure_nn_buffers(e);
+  }
+  if (nn) {
+    ar_status s = ensure_nn_buffers(e);
     if (s) return s;
     s = ensure_maze_table(e, p.n_games);
     if (s) return s;
   }
   CK(cudaEventRecord(e->ev0, e->stream));
-  if (!nn) {
+  if (!nn && !tt_run) {
+    selfplay_uniform_kernel<<<(slots + 3) / 4, 128, smem, e->stream>>>(p);
+    CK(cudaGetLastError());
+    e->launches += 1;
+  } else if (tt_run) {
     tt::Ctx c{};
     c.arena = e->tt_arena;
     c.page_bitmap = e->tt_bitmap;
@@ -1231,11 +1335,24 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
     c.next_game = e->d_next;
     c.summaries = p.summaries; c.positions = p.positions; c.pos_stride = p.pos_stride;
     c.search_out = p.search_out; c.search_only = p.search_only;
+    { const char* v = getenv("AR_TT_MAX_MOVES"); c.max_moves = v ? atoi(v) : 0; }
     c.counters = e->d_counters;
     c.error_flag = e->d_error;
     c.progress = p.progress;
-    const int tslots = (std::min<int>((int)e->tt_slots, std::max(p.n_games, 1)) + TT_BLOCK - 1) / TT_BLOCK * TT_BLOCK;
-    selfplay_tt_kernel<<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->stream>>>(c, tslots);
+    const int tslots = (std::min<int>((int)e->tt_slots, std::max(p.n_games, 1)) + TB_BLOCK - 1) / TB_BLOCK * TB_BLOCK;
+    static const int variant = [] { const char* v = getenv("AR_TT_KERNEL"); return v ? atoi(v) : 1; }();  // 0 lane-bound, 1 block-sorted
+    if (variant == 1) {
+      static const int tb_minb = [] { const char* v = getenv("AR_TB_BLOCKS_PER_SM"); return v ? atoi(v) : 3; }();
+      if (tb_minb >= 4) selfplay_tb_kernel<4><<<tslots / TB_BLOCK, TB_BLOCK, tb_smem_bytes(), e->stream>>>(c, e->tt_arrs);
+      else selfplay_tb_kernel<3><<<tslots / TB_BLOCK, TB_BLOCK, tb_smem_bytes(), e->stream>>>(c, e->tt_arrs);
+    } else {
+    // resident warps per SM (register budget): experiment knob, default 12
+    static const int minb = [] { const char* v = getenv("AR_TT_WARPS_PER_SM"); return v ? atoi(v) : 12; }();
+    if (minb >= 20) selfplay_tt_kernel<20><<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->stream>>>(c, tslots);
+    else if (minb >= 16) selfplay_tt_kernel<16><<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->stream>>>(c, tslots);
+    else if (minb >= 12) selfplay_tt_kernel<12><<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->stream>>>(c, tslots);
+    else selfplay_tt_kernel<8><<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->stream>>>(c, tslots);
+    }
     CK(cudaGetLastError());
     e->launches += 1;
   } else {
@@ -1485,37 +1602,6 @@ ar_status ar_selfplay_run_resident(ar_engine* e, const ar_search_cfg* cfg, ar_st
   return run_resident(e, cfg, nullptr, stats);
 }
 
-// compute_cheese_outcomes (selfplay.rs:415-471) on the host from the downloaded records
-static void attribute_cheese(const ar_game_pod& pod, ar_game_summary& s, const ar_position_record* pos) {
-  int w = pod.width, cells = pod.width * pod.height;
-  int fp1 = s.reserved[0], fp2 = s.reserved[1];
-  uint64_t final_cheese;
-  memcpy(&final_cheese, s.cheese_outcomes, 8);
-  memset(s.cheese_outcomes, 2, sizeof(s.cheese_outcomes));
-  memset(s.reserved, 0, sizeof(s.reserved));
-  int n = (int)s.n_positions;
-  for (int i = 0; i < n; ++i) {
-    uint64_t cur, nxt;
-    memcpy(&cur, pos[i].cheese, 8);
-    int n1, n2;
-    if (i + 1 < n) {
-      memcpy(&nxt, pos[i + 1].cheese, 8);
-      n1 = pos[i + 1].p1_y * w + pos[i + 1].p1_x;
-      n2 = pos[i + 1].p2_y * w + pos[i + 1].p2_x;
-    } else {
-      nxt = final_cheese; n1 = fp1; n2 = fp2;
-    }
-    uint64_t gone = cur & ~nxt;
-    while (gone) {  // almost always empty: visit only the pieces that disappeared
-      const int c = __builtin_ctzll(gone);
-      gone &= gone - 1;
-      if (c >= cells) break;
-      bool a = n1 == c, b = n2 == c;
-      s.cheese_outcomes[c] = (a && b) ? 1 : a ? 0 : b ? 3 : 2;
-    }
-  }
-}
-
 ar_status ar_selfplay_download(ar_engine* e, ar_game_summary* summaries, ar_position_record* positions,
                                int32_t positions_stride) {
   if (!e) return AR_ERR_INVALID_ARG;
@@ -1558,13 +1644,12 @@ ar_status ar_selfplay_download(ar_engine* e, ar_game_summary* summaries, ar_posi
   }
   e->launches += 1;
   e->d2h += (uint64_t)n * sizeof(ar_game_summary) + total * sizeof(ar_position_record);
-  // scatter into the caller's strided array + cheese attribution, split over a few host threads
+  // scatter into the caller's strided array, split over a few host threads
   auto finish = [&](int lo, int hi) {
     for (int i = lo; i < hi; ++i) {
       ar_position_record* dst = positions + (size_t)i * positions_stride;
       if (summaries[i].n_positions)
         memcpy(dst, e->h_dense + off[i], (size_t)summaries[i].n_positions * sizeof(ar_position_record));
-      if (e->last_run_nn) attribute_cheese(e->h_games[i], summaries[i], dst);
     }
   };
   const int n_thr = n >= 4096 ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define AR_ABI_VERSION 1
+#define AR_ABI_VERSION 2
 #define AR_MAX_CELLS 256 /* POD capacity (16x16); kernels in this build accept <= 64 cells */
 #define AR_NUM_ACTIONS 5 /* UP=0 RIGHT=1 DOWN=2 LEFT=3 STAY=4 (pyrat_engine Direction)      */
 
@@ -146,13 +146,21 @@ typedef struct ar_progress {
 typedef struct ar_engine_cfg {
   uint32_t abi_version;      /* AR_ABI_VERSION                                         */
   int32_t device;            /* CUDA ordinal                                           */
-  uint32_t concurrent_games; /* resident game trees (one warp each)                    */
+  uint32_t concurrent_games; /* resident game trees                                    */
   uint32_t pool_nodes;       /* node-pool capacity per tree (<= 65535), 0 = auto       */
   uint32_t max_cells;        /* width*height upper bound for this engine               */
   uint32_t max_turns;        /* upper bound on max_turns (depth stack)                 */
   uint32_t max_batch_size;   /* upper bound on ar_search_cfg.batch_size                */
   uint32_t max_simulations;  /* used for pool auto-sizing                              */
+  uint32_t tree_engine;      /* uniform-prior runs: AR_TREE_WARP (default) or AR_TREE_THREAD */
 } ar_engine_cfg;
+
+/* Two device engines play the uniform-prior path, bit-identically (both are checked against the
+ * oracle).  AR_TREE_WARP: one warp per game tree, fixed node pools, lowest latency per game.
+ * AR_TREE_THREAD: one thread per game tree (32 trees per warp), paged node pools shared by all
+ * resident trees; measured slower on B200 (profiles/r2_summary.md), kept as a selectable engine. */
+#define AR_TREE_WARP 0
+#define AR_TREE_THREAD 1
 
 /* One named f32 tensor of a torch state_dict (host memory). */
 typedef struct ar_tensor_desc {

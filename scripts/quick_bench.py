@@ -1,15 +1,25 @@
+"""Steady-state probe of the uniform self-play kernel: N games (32768 distinct layouts tiled, distinct seeds)
+through CONC resident trees; prints device-timed S_new/s.  usage: quick_bench.py N CONC [REPEATS]"""
+import ctypes as C
 import sys, time
 sys.path.insert(0,'.')
+from alpharat_b200 import _native as N
 from alpharat_b200.engine import Engine, search_cfg
 from alpharat_b200.games import make_games, pods_array
 n=int(sys.argv[1]); conc=int(sys.argv[2])
-specs = make_games(n, width=7, height=7, cheese_count=10, max_turns=50)
-pods = pods_array(specs)
+base = min(n, 32768)
+pods0 = pods_array(make_games(base, width=7, height=7, cheese_count=10, max_turns=50))
+pods = (N.GamePod * n)()
+sz = C.sizeof(N.GamePod)
+for off in range(0, n, base):
+    m = min(base, n - off)
+    C.memmove(C.byref(pods, off * sz), pods0, m * sz)
 cfg = search_cfg(simulations=1897, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103)
 eng = Engine(concurrent_games=conc, max_turns=50, max_batch_size=16, max_simulations=1897)
 eng.selfplay_upload(pods, list(range(n)))
-for it in range(int(sys.argv[3]) if len(sys.argv)>3 else 2):
+for it in range(int(sys.argv[3]) if len(sys.argv)>3 else 1):
     st = eng.selfplay_run_resident(cfg)
+    snew = st.total_nn_evals + st.total_terminals if False else None
     summ, pos = eng.selfplay_download(n, 50)
     npos = sum(summ[i].n_positions for i in range(n))
     snew = npos*1897

@@ -19,6 +19,10 @@ from conftest import oracle_search, oracle_selfplay
 
 pytestmark = pytest.mark.gpu
 
+# Both device engines of the uniform-prior path (include/alpharat_cuda.h: AR_TREE_WARP, AR_TREE_THREAD)
+# are held to the same bit-exact bar.
+ENGINES = pytest.mark.parametrize("tree_engine", ["warp", "thread"])
+
 
 def _bytes(x) -> bytes:
     return bytes(memoryview(x).cast("B"))
@@ -53,14 +57,15 @@ def compare_selfplay(gpu, cpu, n):
             assert_result_equal(pa.search, pb.search, f"game {i} move {t}")
 
 
-def test_selfplay_5x5_config_a(oracle):
-    """BASELINE config 1 (reduced game count): 5x5 open, 5 cheese, 30 turns, 100 sims, batch 8."""
-    n = 256
+@ENGINES
+def test_selfplay_5x5_config_a(oracle, tree_engine):
+    """BASELINE config 1, all 1000 games: 5x5 open, 5 cheese, 30 turns, 100 sims, batch 8."""
+    n = 1000
     specs = make_games(n, width=5, height=5, cheese_count=5, max_turns=30)
     pods = pods_array(specs)
     cfg = search_cfg(simulations=100, batch_size=8)
     seeds = list(range(n))
-    with Engine(concurrent_games=128, max_turns=30, max_batch_size=8, max_simulations=100) as eng:
+    with Engine(concurrent_games=128, max_turns=30, max_batch_size=8, max_simulations=100, tree_engine=tree_engine) as eng:
         gpu = eng.selfplay(pods, cfg, seeds)
     cpu = oracle_selfplay(oracle, pods, cfg, seeds)
     compare_selfplay(gpu, cpu, n)
@@ -70,20 +75,22 @@ def test_selfplay_5x5_config_a(oracle):
     assert gpu[3].new_nodes == cpu[3].new_nodes
 
 
-def test_selfplay_7x7_tuned(oracle):
-    """BASELINE config 2 parameters (7x7_rust_tuned, noise 0) on a handful of games."""
-    n = 24
+@ENGINES
+def test_selfplay_7x7_tuned(oracle, tree_engine):
+    """BASELINE config 2 parameters (7x7_rust_tuned, noise 0), 512 games through 256 resident trees."""
+    n = 512
     specs = make_games(n, width=7, height=7, cheese_count=10, max_turns=50)
     pods = pods_array(specs)
     cfg = search_cfg(simulations=1897, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103)
     seeds = [1000 + i for i in range(n)]
-    with Engine(concurrent_games=n, max_turns=50, max_batch_size=16, max_simulations=1897) as eng:
+    with Engine(concurrent_games=256, max_turns=50, max_batch_size=16, max_simulations=1897, tree_engine=tree_engine) as eng:
         gpu = eng.selfplay(pods, cfg, seeds)
     cpu = oracle_selfplay(oracle, pods, cfg, seeds)
     compare_selfplay(gpu, cpu, n)
 
 
-def test_selfplay_classic_mazes_with_walls_and_mud(oracle):
+@ENGINES
+def test_selfplay_classic_mazes_with_walls_and_mud(oracle, tree_engine):
     """walls, mud timers (the [4,4,4,4,4] stuck outcome), random starts, non-square board."""
     n = 48
     specs = make_games(n, width=7, height=5, cheese_count=6, max_turns=40, maze_type="classic", positions="random",
@@ -91,13 +98,14 @@ def test_selfplay_classic_mazes_with_walls_and_mud(oracle):
     pods = pods_array(specs)
     cfg = search_cfg(simulations=300, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103)
     seeds = [31 * i + 5 for i in range(n)]
-    with Engine(concurrent_games=32, max_turns=40, max_batch_size=16, max_simulations=300) as eng:
+    with Engine(concurrent_games=32, max_turns=40, max_batch_size=16, max_simulations=300, tree_engine=tree_engine) as eng:
         gpu = eng.selfplay(pods, cfg, seeds)
     cpu = oracle_selfplay(oracle, pods, cfg, seeds)
     compare_selfplay(gpu, cpu, n)
 
 
-def test_search_batch_matches_oracle(oracle):
+@ENGINES
+def test_search_batch_matches_oracle(oracle, tree_engine):
     specs = make_games(32, width=5, height=5, cheese_count=5, max_turns=30)
     specs += [
         GameSpec(5, 5, 100, (2, 2), (2, 2), [(0, 0), (4, 4), (0, 4), (4, 0), (1, 3)]),
@@ -110,7 +118,8 @@ def test_search_batch_matches_oracle(oracle):
     for sims, bs in ((10, 8), (50, 8), (100, 8), (200, 8), (100, 1), (300, 16)):
         cfg = search_cfg(simulations=sims, batch_size=bs)
         seeds = [7 * i + sims for i in range(len(specs))]
-        with Engine(concurrent_games=64, max_turns=100, max_batch_size=16, max_simulations=sims, pool_nodes=1024) as eng:
+        with Engine(concurrent_games=64, max_turns=100, max_batch_size=16, max_simulations=sims, pool_nodes=1024,
+                    tree_engine=tree_engine) as eng:
             out = eng.search_batch(pods, cfg, seeds)
         for i in range(len(specs)):
             rc, ref, clean = oracle_search(oracle, pods[i], cfg, seeds[i])
@@ -142,7 +151,8 @@ def test_large_scale_properties():
     assert st.total_games == n
 
 
-def test_selfplay_with_dirichlet_noise(oracle):
+@ENGINES
+def test_selfplay_with_dirichlet_noise(oracle, tree_engine):
     """Production sampling config (`7x7_rust_tuned.yaml`: noise_epsilon 0.25, concentration 10.83).
 
     The Gamma sampler is the oracle's restatement (Marsaglia-Tsang over a polar normal), drawn
@@ -155,7 +165,7 @@ def test_selfplay_with_dirichlet_noise(oracle):
     cfg = search_cfg(simulations=600, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103,
                      noise_epsilon=0.25, noise_concentration=10.83)
     seeds = [5000 + i for i in range(n)]
-    with Engine(concurrent_games=n, max_turns=50, max_batch_size=16, max_simulations=600) as eng:
+    with Engine(concurrent_games=n, max_turns=50, max_batch_size=16, max_simulations=600, tree_engine=tree_engine) as eng:
         gpu = eng.selfplay(pods, cfg, seeds)
         quiet = eng.selfplay(pods, search_cfg(simulations=600, batch_size=16, c_puct=0.512,
                                               fpu_reduction=0.459, force_k=0.103), seeds)
