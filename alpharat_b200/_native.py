@@ -139,6 +139,8 @@ EXPORTED_SYMBOLS = (
     "ar_engine_load_weights", "ar_search_batch", "ar_selfplay_run", "ar_selfplay_upload",
     "ar_selfplay_run_resident", "ar_selfplay_download", "ar_encode_observations",
     "ar_nn_forward", "ar_engine_set_eval_cache",
+    "ar_stream_open", "ar_stream_close", "ar_stream_submit", "ar_stream_collect", "ar_stream_launch",
+    "ar_stream_wait", "ar_stream_elapsed_ms", "ar_stream_times", "ar_selfplay_pack_device",
 )
 
 _LIB = None
@@ -191,6 +193,24 @@ def load_library() -> C.CDLL:
     lib.ar_nn_forward.restype = C.c_int
     lib.ar_engine_set_eval_cache.argtypes = [eng, C.c_uint32]
     lib.ar_engine_set_eval_cache.restype = C.c_int
+    lib.ar_selfplay_pack_device.argtypes = [eng, P(GameSummary), P(C.c_void_p), P(C.c_void_p), P(C.c_uint64)]
+    lib.ar_selfplay_pack_device.restype = C.c_int
+    lib.ar_stream_open.argtypes = [eng, C.c_int32, C.c_int32, C.c_int32]
+    lib.ar_stream_open.restype = C.c_int
+    lib.ar_stream_close.argtypes = [eng]
+    lib.ar_stream_close.restype = None
+    lib.ar_stream_submit.argtypes = [eng, C.c_int32, P(GamePod), C.c_int32, P(SearchCfg), P(C.c_uint64)]
+    lib.ar_stream_submit.restype = C.c_int
+    lib.ar_stream_collect.argtypes = [eng, C.c_int32, P(GameSummary), P(PositionRecord), C.c_int32, P(Stats)]
+    lib.ar_stream_collect.restype = C.c_int
+    lib.ar_stream_launch.argtypes = [eng, C.c_int32, P(SearchCfg)]
+    lib.ar_stream_launch.restype = C.c_int
+    lib.ar_stream_wait.argtypes = [eng, C.c_int32, P(Stats)]
+    lib.ar_stream_wait.restype = C.c_int
+    lib.ar_stream_times.argtypes = [eng, C.c_int32, P(C.c_double), P(C.c_double)]
+    lib.ar_stream_times.restype = C.c_int
+    lib.ar_stream_elapsed_ms.argtypes = [eng, C.c_int32, C.c_int32, P(C.c_double)]
+    lib.ar_stream_elapsed_ms.restype = C.c_int
     if lib.ar_abi_version() != AR_ABI_VERSION:
         raise RuntimeError(f"ABI mismatch: library {lib.ar_abi_version()} != python {AR_ABI_VERSION}")
     _LIB = lib

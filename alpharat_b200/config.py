@@ -55,7 +55,7 @@ class CudaMCTSConfig(_SearchFields):
     backend: Literal["cuda"] = "cuda"
     device_ids: list[int] = Field(default_factory=lambda: [0])
     concurrent_games: int = 4096
-    pool_nodes: int = 0  # 0 = auto (12 * simulations + 1024, capped at 65535)
+    pool_nodes: int = 0  # 0 = auto: max_turns * simulations + 2 nodes per tree when that fits in 70 % of free HBM
     seed: int | None = None
 
     def build_searcher(self, checkpoint: str | None = None, device: str = "cuda"):

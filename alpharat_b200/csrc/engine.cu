@@ -49,6 +49,8 @@ struct RunParams {
   uint32_t max_depth;
   uint32_t batch_cap;
   int n_slots;
+  uint32_t* slot_bitmap;  // streaming launches: blocks claim a group of 4 tree slots here (null: group = blockIdx)
+  int n_groups;
   // bookkeeping
   unsigned int* next_game;
   unsigned long long* counters;  // [0] path_nodes [1] new_nodes
@@ -160,7 +162,34 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(Ru
   int lane = threadIdx.x & 31;
   asm volatile("" : "+r"(lane));
   const int wib = threadIdx.x >> 5;
-  const int slot = blockIdx.x * 4 + wib;
+  // Streaming launches overlap in time (batch b+1 fills the SMs as batch b's last games drain), so a
+  // block cannot own the slots of its blockIdx: it claims a free group of 4 tree slots instead.
+  __shared__ int s_group;
+  int group = blockIdx.x;
+  if (p.slot_bitmap) {
+    if (threadIdx.x == 0) {
+      const int words = (p.n_groups + 31) / 32;
+      int w = (int)(blockIdx.x % words), got = -1;
+      while (got < 0) {
+        for (int t = 0; t < words && got < 0; ++t) {
+          uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&p.slot_bitmap[w]);
+          while (cur != 0xffffffffu) {
+            const int b = __ffs((int)~cur) - 1;
+            if (w * 32 + b >= p.n_groups) break;
+            const uint32_t old = atomicOr(&p.slot_bitmap[w], 1u << b);
+            if (!(old & (1u << b))) { got = w * 32 + b; break; }
+            cur = old | (1u << b);
+          }
+          w = (w + 1 == words) ? 0 : w + 1;
+        }
+        if (got < 0) __nanosleep(2000);  // more resident blocks than groups: wait for a block to leave
+      }
+      s_group = got;
+    }
+    __syncthreads();
+    group = s_group;
+  }
+  const int slot = group * 4 + wib;
   if (slot >= p.n_slots) return;
 
   uint8_t* base = smem + (size_t)wib * warp_smem_bytes(p.max_depth, p.batch_cap);
@@ -283,6 +312,13 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(Ru
         atomicAdd_system((unsigned long long*)&p.progress->nn_evals_completed, tot_nn);
         atomicAdd_system((unsigned int*)&p.progress->games_completed, 1u);
       }
+#ifndef AR_PHASE_TIMING
+      // run totals, so that a caller that only wants throughput needs no record download
+      atomicAdd(&p.counters[2], tot_nn);
+      atomicAdd(&p.counters[3], tot_term);
+      atomicAdd(&p.counters[4], (unsigned long long)n_pos);
+      atomicAdd(&p.counters[5], tot_sims);
+#endif
     }
   }
 #ifdef AR_PHASE_TIMING
@@ -296,8 +332,11 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(Ru
 #endif
     if (cx.error) atomicCAS(p.error_flag, 0, (int)cx.error);
   }
+  if (p.slot_bitmap) {  // n_slots is a multiple of 4 in streaming mode: every warp of the block gets here
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAnd(&p.slot_bitmap[group >> 5], ~(1u << (group & 31)));
+  }
 }
-
 
 
 // =========================================================================================
@@ -344,7 +383,6 @@ __global__ void __launch_bounds__(TT_BLOCK, MIN_BLOCKS) selfplay_tt_kernel(tt::C
   }
   atomicAdd(&c.counters[0], s.path_nodes);
   atomicAdd(&c.counters[1], s.new_nodes);
-  atomicAdd(&c.counters[3], steps);
   if (s.error) atomicCAS(c.error_flag, 0, (int)s.error);
 }
 
@@ -429,7 +467,6 @@ __global__ void __launch_bounds__(TB_BLOCK, MIN_BLOCKS) selfplay_tb_kernel(tt::C
   }
   atomicAdd(&c.counters[0], st[tid].path_nodes);
   atomicAdd(&c.counters[1], st[tid].new_nodes);
-  atomicAdd(&c.counters[3], steps);
   if (st[tid].error) atomicCAS(c.error_flag, 0, (int)st[tid].error);
 }
 
@@ -866,11 +903,44 @@ __global__ void compact_positions_kernel(const ar_position_record* __restrict__ 
 // =========================================================================================
 using namespace ar;
 
+// Everything one batch of games needs on the device and on its way back: inputs, outputs, the work
+// counter the persistent kernel claims games from, a stream and two events.  The engine's blocking API
+// uses `main`; the streaming API (ar_stream_*) keeps several in flight.
+struct BatchBuf {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  ar_game_pod* d_games = nullptr;
+  uint64_t* d_seeds = nullptr;
+  ar_game_summary* d_summaries = nullptr;
+  ar_position_record* d_positions = nullptr;
+  int cap_games = 0, cap_stride = 0;
+  ar_position_record* d_dense = nullptr;   // packed records for the download
+  ar_position_record* h_dense = nullptr;   // pinned staging
+  uint32_t* d_offsets = nullptr;
+  size_t cap_dense = 0;
+  int cap_offsets = 0;
+  int n_resident = 0, resident_stride = 0;
+  bool resident_valid = false;  // d_games / d_seeds hold an uploaded batch (search and evaluator calls overwrite them)
+  std::vector<ar_game_pod> h_games;  // board sizes of the resident batch (evaluator shape check)
+  unsigned int* d_next = nullptr;
+  unsigned long long* d_counters = nullptr;
+  int* d_error = nullptr;
+  uint64_t h2d = 0, d2h = 0, launches = 0;
+  // streaming only
+  ar_game_pod* h_games_pinned = nullptr;
+  uint64_t* h_seeds_pinned = nullptr;
+  bool in_flight = false;
+  std::chrono::steady_clock::time_point t_submit;
+};
+
 struct ar_engine {
   ar_engine_cfg cfg{};
   int device = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  BatchBuf main;
+  BatchBuf* cur = &main;                       // the batch the internal helpers operate on
+  std::vector<BatchBuf*> sbufs;                // ar_stream_open
+  uint32_t* d_slot_bitmap = nullptr;           // slot groups (4 trees) in use by streaming launches
+  cudaEvent_t ev_base = nullptr;               // time origin of ar_stream_times
   cudaStream_t stream2 = nullptr;              // second slot group of the NN-guided loop
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
@@ -890,26 +960,10 @@ struct ar_engine {
   ar_search_cfg coll_cfg{};
   uint32_t coll_len = 0;
   bool coll_valid = false;
-  // run buffers
-  ar_game_pod* d_games = nullptr;
-  uint64_t* d_seeds = nullptr;
-  ar_game_summary* d_summaries = nullptr;
-  ar_position_record* d_positions = nullptr;
   ar_search_result* d_search = nullptr;
-  int cap_games = 0, cap_stride = 0, cap_search = 0;
-  ar_position_record* d_dense = nullptr;   // packed records for the download
-  ar_position_record* h_dense = nullptr;   // pinned staging
-  uint32_t* d_offsets = nullptr;
-  size_t cap_dense = 0;
-  int cap_offsets = 0;
-  int n_resident = 0, resident_stride = 0;
-  std::vector<ar_game_pod> h_games;  // kept for cheese-outcome attribution
-  unsigned int* d_next = nullptr;
-  unsigned long long* d_counters = nullptr;
-  int* d_error = nullptr;
+  int cap_search = 0;
   ar_progress* h_progress = nullptr;  // mapped pinned
   ar_progress* d_progress = nullptr;
-  uint64_t h2d = 0, d2h = 0, launches = 0;
   // leaf evaluator
   int arch = AR_ARCH_UNIFORM;
   int nn_width = 0, nn_height = 0;
@@ -955,8 +1009,8 @@ static ar_status ensure_coll_table(ar_engine* e, const ar_search_cfg& c) {
   }
   std::vector<uint16_t> t = ar_host::collision_table(c, e->coll_len);
   CK(cudaMemcpyAsync(e->coll_table, t.data(), t.size() * sizeof(uint16_t), cudaMemcpyHostToDevice,
-                     e->stream));
-  CK(cudaStreamSynchronize(e->stream));
+                     e->cur->stream));
+  CK(cudaStreamSynchronize(e->cur->stream));
   e->coll_cfg = c;
   e->coll_valid = true;
   return AR_OK;
@@ -1020,14 +1074,15 @@ static void pod_to_row(const ar_game_pod& g, uint32_t game_idx, EvalRow& r) {
 static ar_status stage_rows(ar_engine* e, const ar_game_pod* games, int n) {
   ar_status s = validate_games(e, games, n);
   if (s) return s;
-  if (n > e->cap_games) {
-    cudaFree(e->d_games); cudaFree(e->d_seeds); cudaFree(e->d_summaries); cudaFree(e->d_positions);
-    e->d_games = nullptr; e->d_seeds = nullptr; e->d_summaries = nullptr; e->d_positions = nullptr;
-    CK(cudaMalloc(&e->d_games, (size_t)n * sizeof(ar_game_pod)));
-    CK(cudaMalloc(&e->d_seeds, (size_t)n * sizeof(uint64_t)));
-    CK(cudaMalloc(&e->d_summaries, (size_t)n * sizeof(ar_game_summary)));
-    e->cap_games = n;
-    e->cap_stride = 0;
+  e->cur->resident_valid = false;  // the staging below reuses the upload buffers
+  if (n > e->cur->cap_games) {
+    cudaFree(e->cur->d_games); cudaFree(e->cur->d_seeds); cudaFree(e->cur->d_summaries); cudaFree(e->cur->d_positions);
+    e->cur->d_games = nullptr; e->cur->d_seeds = nullptr; e->cur->d_summaries = nullptr; e->cur->d_positions = nullptr;
+    CK(cudaMalloc(&e->cur->d_games, (size_t)n * sizeof(ar_game_pod)));
+    CK(cudaMalloc(&e->cur->d_seeds, (size_t)n * sizeof(uint64_t)));
+    CK(cudaMalloc(&e->cur->d_summaries, (size_t)n * sizeof(ar_game_summary)));
+    e->cur->cap_games = n;
+    e->cur->cap_stride = 0;
   }
   if (n > e->cap_rows) {
     cudaFree(e->d_rows); cudaFree(e->d_nn_out);
@@ -1038,10 +1093,58 @@ static ar_status stage_rows(ar_engine* e, const ar_game_pod* games, int n) {
   }
   std::vector<EvalRow> rows(n);
   for (int i = 0; i < n; ++i) pod_to_row(games[i], (uint32_t)i, rows[i]);
-  CK(cudaMemcpyAsync(e->d_games, games, (size_t)n * sizeof(ar_game_pod), cudaMemcpyHostToDevice, e->stream));
-  CK(cudaMemcpyAsync(e->d_rows, rows.data(), (size_t)n * sizeof(EvalRow), cudaMemcpyHostToDevice, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpyAsync(e->cur->d_games, games, (size_t)n * sizeof(ar_game_pod), cudaMemcpyHostToDevice, e->cur->stream));
+  CK(cudaMemcpyAsync(e->d_rows, rows.data(), (size_t)n * sizeof(EvalRow), cudaMemcpyHostToDevice, e->cur->stream));
+  CK(cudaStreamSynchronize(e->cur->stream));
   return AR_OK;
+}
+
+static void batch_free(BatchBuf& b) {
+  cudaFree(b.d_games); cudaFree(b.d_seeds); cudaFree(b.d_summaries); cudaFree(b.d_positions);
+  cudaFree(b.d_next); cudaFree(b.d_counters); cudaFree(b.d_error);
+  cudaFree(b.d_dense); cudaFree(b.d_offsets);
+  if (b.h_dense) cudaFreeHost(b.h_dense);
+  if (b.h_games_pinned) cudaFreeHost(b.h_games_pinned);
+  if (b.h_seeds_pinned) cudaFreeHost(b.h_seeds_pinned);
+  if (b.ev0) cudaEventDestroy(b.ev0);
+  if (b.ev1) cudaEventDestroy(b.ev1);
+  if (b.stream) cudaStreamDestroy(b.stream);
+  b = BatchBuf();
+}
+
+static cudaError_t batch_init(BatchBuf& b) {
+  cudaError_t ce = cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&b.ev0);
+  if (ce == cudaSuccess) ce = cudaEventCreate(&b.ev1);
+  if (ce == cudaSuccess) ce = cudaMalloc(&b.d_next, sizeof(unsigned int));
+  if (ce == cudaSuccess) ce = cudaMalloc(&b.d_counters, 8 * sizeof(unsigned long long));
+  if (ce == cudaSuccess) ce = cudaMalloc(&b.d_error, sizeof(int));
+  return ce;
+}
+
+// SelfPlayStats::from_games (selfplay.rs:212-224)
+static void fill_game_stats(ar_stats* stats, const ar_game_summary* summaries, int n) {
+  stats->total_games = 0; stats->total_positions = 0; stats->total_simulations = 0;
+  stats->total_nn_evals = 0; stats->total_terminals = 0; stats->total_collisions = 0;
+  stats->total_cheese_collected = 0; stats->total_cheese_available = 0;
+  stats->p1_wins = stats->p2_wins = stats->draws = 0;
+  stats->min_turns = 0xffffffffu;
+  stats->max_turns = 0;
+  for (int i = 0; i < n; ++i) {
+    const ar_game_summary& g = summaries[i];
+    stats->total_games += 1;
+    stats->total_positions += g.n_positions;
+    stats->total_simulations += g.total_simulations;
+    stats->total_nn_evals += g.total_nn_evals;
+    stats->total_terminals += g.total_terminals;
+    stats->total_collisions += g.total_collisions;
+    stats->total_cheese_collected += g.final_p1_score + g.final_p2_score;
+    stats->total_cheese_available += g.cheese_available;
+    stats->min_turns = std::min(stats->min_turns, g.n_positions);
+    stats->max_turns = std::max(stats->max_turns, g.n_positions);
+    if (g.result == 1) stats->p1_wins++; else if (g.result == 2) stats->p2_wins++; else stats->draws++;
+  }
+  if (n == 0) stats->min_turns = 0;
 }
 
 extern "C" {
@@ -1092,17 +1195,12 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
     cudaError_t _e = (call);                                                           \
     if (_e != cudaSuccess) return fail(AR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
   } while (0)
-  CKC(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CKC(batch_init(e->main));
   CKC(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
   CKC(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
   CKC(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-  CKC(cudaEventCreate(&e->ev0));
-  CKC(cudaEventCreate(&e->ev1));
   e->coll_len = (uint32_t)std::min<uint64_t>((uint64_t)e->node_cap + 2, 1u << 20);
   CKC(cudaMalloc(&e->coll_table, (size_t)e->coll_len * sizeof(uint16_t)));
-  CKC(cudaMalloc(&e->d_next, sizeof(unsigned int)));
-  CKC(cudaMalloc(&e->d_counters, 8 * sizeof(unsigned long long)));
-  CKC(cudaMalloc(&e->d_error, sizeof(int)));
   CKC(cudaHostAlloc(&e->h_progress, sizeof(ar_progress), cudaHostAllocMapped));
   CKC(cudaHostGetDevicePointer(&e->d_progress, e->h_progress, 0));
   CKC(cudaFuncSetAttribute(selfplay_uniform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1112,26 +1210,28 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
   return AR_OK;
 }
 
+void ar_stream_close(ar_engine* e);
+
 void ar_engine_destroy(ar_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  ar_stream_close(e);
   cudaFree(e->pools); cudaFree(e->path_bufs); cudaFree(e->remaps); cudaFree(e->coll_table);
   cudaFree(e->tt_arena); cudaFree(e->tt_bitmap); cudaFree(e->tt_page_tables); cudaFree(e->tt_arrs);
-  cudaFree(e->d_games); cudaFree(e->d_seeds); cudaFree(e->d_summaries); cudaFree(e->d_positions);
-  cudaFree(e->d_search); cudaFree(e->d_next); cudaFree(e->d_counters); cudaFree(e->d_error);
+  cudaFree(e->d_slot_bitmap);
+  batch_free(e->main);
+  cudaFree(e->d_search);
   cudaFree(e->d_rows); cudaFree(e->d_nn_out);
-  cudaFree(e->d_dense); cudaFree(e->d_offsets); cudaFree(e->d_maze_tab);
-  if (e->h_dense) cudaFreeHost(e->h_dense);
+  cudaFree(e->d_maze_tab);
   cudaFree(e->d_slots); cudaFree(e->d_tp_store); cudaFree(e->d_queue); cudaFree(e->d_queue_out); cudaFree(e->d_n_rows);
   cudaFree(e->d_cache); cudaFree(e->d_key_store); cudaFree(e->d_board_store);
   delete e->eval;
   if (e->h_progress) cudaFreeHost(e->h_progress);
-  if (e->ev0) cudaEventDestroy(e->ev0);
-  if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->ev_base) cudaEventDestroy(e->ev_base);
   if (e->stream2) cudaStreamDestroy(e->stream2);
-  if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
 
@@ -1165,7 +1265,7 @@ ar_status ar_engine_load_weights(ar_engine* e, int32_t arch, int32_t width, int3
 ar_status ar_engine_set_eval_cache(ar_engine* e, uint32_t entries_per_tree) {
   if (!e) return AR_ERR_INVALID_ARG;
   CK(cudaSetDevice(e->device));
-  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaStreamSynchronize(e->cur->stream));
   cudaFree(e->d_cache);
   e->d_cache = nullptr;
   e->cache_entries = 0;
@@ -1253,13 +1353,13 @@ static RunParams make_params(ar_engine* e, const ar_search_cfg* cfg) {
   p.max_depth = e->max_depth;
   p.batch_cap = e->batch_cap;
   p.n_slots = e->n_slots;
-  p.next_game = e->d_next;
-  p.counters = e->d_counters;
-  p.error_flag = e->d_error;
+  p.next_game = e->cur->d_next;
+  p.counters = e->cur->d_counters;
+  p.error_flag = e->cur->d_error;
   return p;
 }
 
-// (Re)build the evaluators' per-game maze table for the n games resident in e->d_games.
+// (Re)build the evaluators' per-game maze table for the n games resident in e->cur->d_games.
 static ar_status ensure_maze_table(ar_engine* e, int n) {
   if (n > e->cap_maze) {
     cudaFree(e->d_maze_tab);
@@ -1267,7 +1367,7 @@ static ar_status ensure_maze_table(ar_engine* e, int n) {
     CK(cudaMalloc(&e->d_maze_tab, (size_t)n * MAZE_TAB_STRIDE * sizeof(uint16_t)));
     e->cap_maze = n;
   }
-  CK(build_maze_table(e->d_games, n, e->d_maze_tab, e->stream));
+  CK(build_maze_table(e->cur->d_games, n, e->d_maze_tab, e->cur->stream));
   return AR_OK;
 }
 
@@ -1285,9 +1385,9 @@ static ar_status ensure_nn_buffers(ar_engine* e) {
 }
 
 static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_progress, float* ms) {
-  CK(cudaMemsetAsync(e->d_next, 0, sizeof(unsigned int), e->stream));
-  CK(cudaMemsetAsync(e->d_counters, 0, 8 * sizeof(unsigned long long), e->stream));
-  CK(cudaMemsetAsync(e->d_error, 0, sizeof(int), e->stream));
+  CK(cudaMemsetAsync(e->cur->d_next, 0, sizeof(unsigned int), e->cur->stream));
+  CK(cudaMemsetAsync(e->cur->d_counters, 0, 8 * sizeof(unsigned long long), e->cur->stream));
+  CK(cudaMemsetAsync(e->cur->d_error, 0, sizeof(int), e->cur->stream));
   memset((void*)e->h_progress, 0, sizeof(ar_progress));
   p.progress = user_progress ? e->d_progress : nullptr;
   size_t smem = 4 * warp_smem_bytes(e->max_depth, e->batch_cap);
@@ -1299,8 +1399,8 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
     ar_status s = ensure_tt(e);
     if (s) return s;
     // every launch starts with only the trees' own first pages taken: bits [0, tt_slots)
-    CK(cudaMemsetAsync(e->tt_bitmap, 0, (size_t)e->tt_bitmap_words * sizeof(uint32_t), e->stream));
-    CK(cudaMemsetAsync(e->tt_bitmap, 0xff, (size_t)e->tt_slots / 8, e->stream));
+    CK(cudaMemsetAsync(e->tt_bitmap, 0, (size_t)e->tt_bitmap_words * sizeof(uint32_t), e->cur->stream));
+    CK(cudaMemsetAsync(e->tt_bitmap, 0xff, (size_t)e->tt_slots / 8, e->cur->stream));
   }
   if (!tt_run) {
     ar_status s = ensure_nn_pools(e);
@@ -1313,11 +1413,11 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
     s = ensure_maze_table(e, p.n_games);
     if (s) return s;
   }
-  CK(cudaEventRecord(e->ev0, e->stream));
+  CK(cudaEventRecord(e->cur->ev0, e->cur->stream));
   if (!nn && !tt_run) {
-    selfplay_uniform_kernel<<<(slots + 3) / 4, 128, smem, e->stream>>>(p);
+    selfplay_uniform_kernel<<<(slots + 3) / 4, 128, smem, e->cur->stream>>>(p);
     CK(cudaGetLastError());
-    e->launches += 1;
+    e->cur->launches += 1;
   } else if (tt_run) {
     tt::Ctx c{};
     c.arena = e->tt_arena;
@@ -1332,29 +1432,29 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
     c.sp.noise_epsilon = p.sp.noise_epsilon; c.sp.noise_concentration = p.sp.noise_concentration;
     c.sp.n_sims = p.sp.n_sims; c.sp.batch_size = p.sp.batch_size;
     c.games = p.games; c.seeds = p.seeds; c.n_games = p.n_games;
-    c.next_game = e->d_next;
+    c.next_game = e->cur->d_next;
     c.summaries = p.summaries; c.positions = p.positions; c.pos_stride = p.pos_stride;
     c.search_out = p.search_out; c.search_only = p.search_only;
     { const char* v = getenv("AR_TT_MAX_MOVES"); c.max_moves = v ? atoi(v) : 0; }
-    c.counters = e->d_counters;
-    c.error_flag = e->d_error;
+    c.counters = e->cur->d_counters;
+    c.error_flag = e->cur->d_error;
     c.progress = p.progress;
     const int tslots = (std::min<int>((int)e->tt_slots, std::max(p.n_games, 1)) + TB_BLOCK - 1) / TB_BLOCK * TB_BLOCK;
     static const int variant = [] { const char* v = getenv("AR_TT_KERNEL"); return v ? atoi(v) : 1; }();  // 0 lane-bound, 1 block-sorted
     if (variant == 1) {
       static const int tb_minb = [] { const char* v = getenv("AR_TB_BLOCKS_PER_SM"); return v ? atoi(v) : 3; }();
-      if (tb_minb >= 4) selfplay_tb_kernel<4><<<tslots / TB_BLOCK, TB_BLOCK, tb_smem_bytes(), e->stream>>>(c, e->tt_arrs);
-      else selfplay_tb_kernel<3><<<tslots / TB_BLOCK, TB_BLOCK, tb_smem_bytes(), e->stream>>>(c, e->tt_arrs);
+      if (tb_minb >= 4) selfplay_tb_kernel<4><<<tslots / TB_BLOCK, TB_BLOCK, tb_smem_bytes(), e->cur->stream>>>(c, e->tt_arrs);
+      else selfplay_tb_kernel<3><<<tslots / TB_BLOCK, TB_BLOCK, tb_smem_bytes(), e->cur->stream>>>(c, e->tt_arrs);
     } else {
     // resident warps per SM (register budget): experiment knob, default 12
     static const int minb = [] { const char* v = getenv("AR_TT_WARPS_PER_SM"); return v ? atoi(v) : 12; }();
-    if (minb >= 20) selfplay_tt_kernel<20><<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->stream>>>(c, tslots);
-    else if (minb >= 16) selfplay_tt_kernel<16><<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->stream>>>(c, tslots);
-    else if (minb >= 12) selfplay_tt_kernel<12><<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->stream>>>(c, tslots);
-    else selfplay_tt_kernel<8><<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->stream>>>(c, tslots);
+    if (minb >= 20) selfplay_tt_kernel<20><<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->cur->stream>>>(c, tslots);
+    else if (minb >= 16) selfplay_tt_kernel<16><<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->cur->stream>>>(c, tslots);
+    else if (minb >= 12) selfplay_tt_kernel<12><<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->cur->stream>>>(c, tslots);
+    else selfplay_tt_kernel<8><<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->cur->stream>>>(c, tslots);
     }
     CK(cudaGetLastError());
-    e->launches += 1;
+    e->cur->launches += 1;
   } else {
     NnParams q{};
     q.slots = e->d_slots;
@@ -1373,12 +1473,12 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
       // a run starts with an empty cache: game indices and weights may have changed since the last one
       q.cache = e->d_cache;
       q.cache_mask = e->cache_entries - 1;
-      CK(cudaMemsetAsync(e->d_cache, 0, (size_t)slots * e->cache_entries * sizeof(CacheEnt), e->stream));
+      CK(cudaMemsetAsync(e->d_cache, 0, (size_t)slots * e->cache_entries * sizeof(CacheEnt), e->cur->stream));
     }
-    CK(cudaMemsetAsync(e->d_n_rows, 0, 4 * sizeof(uint32_t), e->stream));
-    nn_init_slots_kernel<<<(slots + 127) / 128, 128, 0, e->stream>>>(e->d_slots, slots);
+    CK(cudaMemsetAsync(e->d_n_rows, 0, 4 * sizeof(uint32_t), e->cur->stream));
+    nn_init_slots_kernel<<<(slots + 127) / 128, 128, 0, e->cur->stream>>>(e->d_slots, slots);
     CK(cudaGetLastError());
-    e->launches += 1;
+    e->cur->launches += 1;
     // With more slots than one wave of warps (148 SMs x 28), the slots are split into two groups that step on
     // two streams: a step is bulk-synchronous (tree kernel, then evaluator), so while one group's stragglers
     // finish or its leaves are being scored, the other group's tree kernel fills the SMs (config 3, 16384
@@ -1387,7 +1487,7 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
     // the global slot.
     const int n_groups = slots >= 8192 ? 2 : 1;
     NnParams qs[2] = {q, q};
-    cudaStream_t streams[2] = {e->stream, e->stream2};
+    cudaStream_t streams[2] = {e->cur->stream, e->stream2};
     for (int g = 0; g < n_groups; ++g) {
       const int s0 = n_groups == 2 ? ((slots / 2 + 3) & ~3) : slots;
       qs[g].slot_begin = g ? s0 : 0;
@@ -1403,11 +1503,11 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
     const int check_every = 32;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
-    cudaError_t cap = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+    cudaError_t cap = cudaStreamBeginCapture(e->cur->stream, cudaStreamCaptureModeThreadLocal);
     if (cap == cudaSuccess) {
       cudaError_t in_cap = cudaSuccess;
       if (n_groups == 2) {
-        in_cap = cudaEventRecord(e->ev_fork, e->stream);
+        in_cap = cudaEventRecord(e->ev_fork, e->cur->stream);
         if (in_cap == cudaSuccess) in_cap = cudaStreamWaitEvent(e->stream2, e->ev_fork, 0);
       }
       for (int it = 0; it < check_every && in_cap == cudaSuccess; ++it) {
@@ -1419,14 +1519,14 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
           in_cap = cudaGetLastError();
           if (in_cap != cudaSuccess) break;
           in_cap = e->eval->forward(qg.rows, qg.n_rows, (int)qg.max_rows, p.games, e->d_maze_tab,
-                                    const_cast<float*>(qg.nn_out), e->d_error, streams[g]);
+                                    const_cast<float*>(qg.nn_out), e->cur->d_error, streams[g]);
         }
       }
       if (n_groups == 2 && in_cap == cudaSuccess) {
         in_cap = cudaEventRecord(e->ev_join, e->stream2);
-        if (in_cap == cudaSuccess) in_cap = cudaStreamWaitEvent(e->stream, e->ev_join, 0);
+        if (in_cap == cudaSuccess) in_cap = cudaStreamWaitEvent(e->cur->stream, e->ev_join, 0);
       }
-      cap = cudaStreamEndCapture(e->stream, &graph);
+      cap = cudaStreamEndCapture(e->cur->stream, &graph);
       if (in_cap != cudaSuccess) cap = in_cap;
       if (cap == cudaSuccess) cap = cudaGraphInstantiate(&gexec, graph, 0);
     }
@@ -1437,14 +1537,14 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
     }
     ar_status loop_status = AR_OK;
     for (;;) {
-      cudaError_t le = cudaGraphLaunch(gexec, e->stream);
-      e->launches += 2 * check_every * n_groups;
+      cudaError_t le = cudaGraphLaunch(gexec, e->cur->stream);
+      e->cur->launches += 2 * check_every * n_groups;
       e->nn_steps += check_every;
       uint32_t h[2] = {0, 0};
       int herr = 0;
-      if (le == cudaSuccess) le = cudaMemcpyAsync(h, e->d_n_rows, sizeof(h), cudaMemcpyDeviceToHost, e->stream);
-      if (le == cudaSuccess) le = cudaMemcpyAsync(&herr, e->d_error, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
-      if (le == cudaSuccess) le = cudaStreamSynchronize(e->stream);
+      if (le == cudaSuccess) le = cudaMemcpyAsync(h, e->d_n_rows, sizeof(h), cudaMemcpyDeviceToHost, e->cur->stream);
+      if (le == cudaSuccess) le = cudaMemcpyAsync(&herr, e->cur->d_error, sizeof(int), cudaMemcpyDeviceToHost, e->cur->stream);
+      if (le == cudaSuccess) le = cudaStreamSynchronize(e->cur->stream);
       if (le != cudaSuccess) {
         e->err = std::string("NN step: ") + cudaGetErrorString(le);
         loop_status = AR_ERR_CUDA;
@@ -1457,18 +1557,18 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
     cudaGraphDestroy(graph);
     if (loop_status != AR_OK) return loop_status;
   }
-  CK(cudaEventRecord(e->ev1, e->stream));
+  CK(cudaEventRecord(e->cur->ev1, e->cur->stream));
   if (user_progress && !nn) {
-    while (cudaEventQuery(e->ev1) == cudaErrorNotReady) {
+    while (cudaEventQuery(e->cur->ev1) == cudaErrorNotReady) {
       memcpy((void*)user_progress, (const void*)e->h_progress, sizeof(ar_progress));
       std::this_thread::sleep_for(std::chrono::milliseconds(2));
     }
   }
-  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaStreamSynchronize(e->cur->stream));
   if (user_progress) memcpy((void*)user_progress, (const void*)e->h_progress, sizeof(ar_progress));
-  CK(cudaEventElapsedTime(ms, e->ev0, e->ev1));
+  CK(cudaEventElapsedTime(ms, e->cur->ev0, e->cur->ev1));
   int herr = 0;
-  CK(cudaMemcpy(&herr, e->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&herr, e->cur->d_error, sizeof(int), cudaMemcpyDeviceToHost));
   if (herr != 0) {
     e->err = "device reported status " + std::to_string(herr) +
              (herr == AR_ERR_POOL_OVERFLOW ? " (node pool / depth stack / eval queue exhausted: raise pool_nodes or max_turns)"
@@ -1497,14 +1597,15 @@ ar_status ar_search_batch(ar_engine* e, const ar_game_pod* games, int32_t n, con
       }
   s = ensure_coll_table(e, *cfg);
   if (s) return s;
-  if (n > e->cap_games) {
-    cudaFree(e->d_games); cudaFree(e->d_seeds); cudaFree(e->d_summaries);
-    e->d_games = nullptr; e->d_seeds = nullptr; e->d_summaries = nullptr;
-    CK(cudaMalloc(&e->d_games, (size_t)n * sizeof(ar_game_pod)));
-    CK(cudaMalloc(&e->d_seeds, (size_t)n * sizeof(uint64_t)));
-    CK(cudaMalloc(&e->d_summaries, (size_t)n * sizeof(ar_game_summary)));
-    e->cap_games = n;
-    e->cap_stride = 0;
+  e->cur->resident_valid = false;  // the search reuses the upload buffers
+  if (n > e->cur->cap_games) {
+    cudaFree(e->cur->d_games); cudaFree(e->cur->d_seeds); cudaFree(e->cur->d_summaries);
+    e->cur->d_games = nullptr; e->cur->d_seeds = nullptr; e->cur->d_summaries = nullptr;
+    CK(cudaMalloc(&e->cur->d_games, (size_t)n * sizeof(ar_game_pod)));
+    CK(cudaMalloc(&e->cur->d_seeds, (size_t)n * sizeof(uint64_t)));
+    CK(cudaMalloc(&e->cur->d_summaries, (size_t)n * sizeof(ar_game_summary)));
+    e->cur->cap_games = n;
+    e->cur->cap_stride = 0;
   }
   if (n > e->cap_search) {
     cudaFree(e->d_search);
@@ -1512,10 +1613,10 @@ ar_status ar_search_batch(ar_engine* e, const ar_game_pod* games, int32_t n, con
     CK(cudaMalloc(&e->d_search, (size_t)n * sizeof(ar_search_result)));
     e->cap_search = n;
   }
-  CK(cudaMemcpyAsync(e->d_games, games, (size_t)n * sizeof(ar_game_pod), cudaMemcpyHostToDevice, e->stream));
-  CK(cudaMemcpyAsync(e->d_seeds, seeds, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaMemcpyAsync(e->cur->d_games, games, (size_t)n * sizeof(ar_game_pod), cudaMemcpyHostToDevice, e->cur->stream));
+  CK(cudaMemcpyAsync(e->cur->d_seeds, seeds, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, e->cur->stream));
   RunParams p = make_params(e, cfg);
-  p.games = e->d_games; p.seeds = e->d_seeds; p.n_games = n;
+  p.games = e->cur->d_games; p.seeds = e->cur->d_seeds; p.n_games = n;
   p.search_only = 1; p.search_out = e->d_search;
   float ms = 0;
   s = launch_and_wait(e, p, nullptr, &ms);
@@ -1532,47 +1633,52 @@ ar_status ar_selfplay_upload(ar_engine* e, const ar_game_pod* games, int32_t n, 
   if (n > 0 && !seeds) { e->err = "seeds is NULL"; return AR_ERR_INVALID_ARG; }
   int stride = 1;
   for (int i = 0; i < n; ++i) stride = std::max<int>(stride, games[i].max_turns);
-  if (n > e->cap_games || stride > e->cap_stride) {
-    cudaFree(e->d_games); cudaFree(e->d_seeds); cudaFree(e->d_summaries); cudaFree(e->d_positions);
-    e->d_games = nullptr; e->d_seeds = nullptr; e->d_summaries = nullptr; e->d_positions = nullptr;
+  if (n > e->cur->cap_games || stride > e->cur->cap_stride) {
+    cudaFree(e->cur->d_games); cudaFree(e->cur->d_seeds); cudaFree(e->cur->d_summaries); cudaFree(e->cur->d_positions);
+    e->cur->d_games = nullptr; e->cur->d_seeds = nullptr; e->cur->d_summaries = nullptr; e->cur->d_positions = nullptr;
     int cap = std::max(n, 1);
-    CK(cudaMalloc(&e->d_games, (size_t)cap * sizeof(ar_game_pod)));
-    CK(cudaMalloc(&e->d_seeds, (size_t)cap * sizeof(uint64_t)));
-    CK(cudaMalloc(&e->d_summaries, (size_t)cap * sizeof(ar_game_summary)));
-    CK(cudaMalloc(&e->d_positions, (size_t)cap * stride * sizeof(ar_position_record)));
-    e->cap_games = cap;
-    e->cap_stride = stride;
+    CK(cudaMalloc(&e->cur->d_games, (size_t)cap * sizeof(ar_game_pod)));
+    CK(cudaMalloc(&e->cur->d_seeds, (size_t)cap * sizeof(uint64_t)));
+    CK(cudaMalloc(&e->cur->d_summaries, (size_t)cap * sizeof(ar_game_summary)));
+    CK(cudaMalloc(&e->cur->d_positions, (size_t)cap * stride * sizeof(ar_position_record)));
+    e->cur->cap_games = cap;
+    e->cur->cap_stride = stride;
   }
   if (n > 0) {
-    CK(cudaMemcpyAsync(e->d_games, games, (size_t)n * sizeof(ar_game_pod), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->d_seeds, seeds, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpyAsync(e->cur->d_games, games, (size_t)n * sizeof(ar_game_pod), cudaMemcpyHostToDevice, e->cur->stream));
+    CK(cudaMemcpyAsync(e->cur->d_seeds, seeds, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, e->cur->stream));
+    CK(cudaStreamSynchronize(e->cur->stream));
   }
-  e->h_games.assign(games, games + n);
-  e->n_resident = n;
-  e->resident_stride = e->cap_stride;
-  e->h2d += (uint64_t)n * (sizeof(ar_game_pod) + sizeof(uint64_t));
+  e->cur->h_games.assign(games, games + n);
+  e->cur->resident_valid = true;
+  e->cur->n_resident = n;
+  e->cur->resident_stride = e->cur->cap_stride;
+  e->cur->h2d += (uint64_t)n * (sizeof(ar_game_pod) + sizeof(uint64_t));
   return AR_OK;
 }
 
 static ar_status run_resident(ar_engine* e, const ar_search_cfg* cfg, ar_progress* progress, ar_stats* stats) {
+  if (!e->cur->resident_valid) {
+    e->err = "no uploaded batch: ar_selfplay_upload must be the last call that staged games on this engine";
+    return AR_ERR_INVALID_ARG;
+  }
   ar_status s = validate_cfg(e, cfg);
   if (s) return s;
   s = ensure_coll_table(e, *cfg);
   if (s) return s;
   if (e->arch != AR_ARCH_UNIFORM)
-    for (const ar_game_pod& g : e->h_games)
+    for (const ar_game_pod& g : e->cur->h_games)
       if (g.width != e->nn_width || g.height != e->nn_height) {
         e->err = "game board size does not match the loaded evaluator";
         return AR_ERR_INVALID_ARG;
       }
-  int n = e->n_resident;
+  int n = e->cur->n_resident;
   float ms = 0;
-  e->launches = 0;
+  e->cur->launches = 0;
   RunParams p = make_params(e, cfg);
   if (n > 0) {
-    p.games = e->d_games; p.seeds = e->d_seeds; p.n_games = n;
-    p.summaries = e->d_summaries; p.positions = e->d_positions; p.pos_stride = e->resident_stride;
+    p.games = e->cur->d_games; p.seeds = e->cur->d_seeds; p.n_games = n;
+    p.summaries = e->cur->d_summaries; p.positions = e->cur->d_positions; p.pos_stride = e->cur->resident_stride;
     p.search_only = 0;
     auto t0 = std::chrono::steady_clock::now();
     s = launch_and_wait(e, p, progress, &ms);
@@ -1581,11 +1687,11 @@ static ar_status run_resident(ar_engine* e, const ar_search_cfg* cfg, ar_progres
   }
   if (stats) {
     unsigned long long c[8] = {0};
-    if (n > 0) CK(cudaMemcpy(c, e->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+    if (n > 0) CK(cudaMemcpy(c, e->cur->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
     stats->device_ms = ms;
     stats->path_nodes = c[0];
     stats->new_nodes = c[1];
-    stats->kernel_launches = e->launches;
+    stats->kernel_launches = e->cur->launches;
     stats->cache_hits = c[6];
     stats->cache_misses = c[7];
 #ifdef AR_PHASE_TIMING
@@ -1602,54 +1708,72 @@ ar_status ar_selfplay_run_resident(ar_engine* e, const ar_search_cfg* cfg, ar_st
   return run_resident(e, cfg, nullptr, stats);
 }
 
+// Pack the resident batch's records on the device: game-major, n_positions records per game.  Needs the
+// game lengths on the host (`summaries` receives all summaries); `off` gets the record offset of every game.
+static ar_status pack_records(ar_engine* e, ar_game_summary* summaries, int positions_stride,
+                              std::vector<uint32_t>& off) {
+  BatchBuf* b = e->cur;
+  const int n = b->n_resident;
+  CK(cudaMemcpy(summaries, b->d_summaries, (size_t)n * sizeof(ar_game_summary), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i)
+    if (positions_stride > 0 && (int)summaries[i].n_positions > positions_stride) {
+      e->err = "positions_stride smaller than a game's length";
+      return AR_ERR_INVALID_ARG;
+    }
+  off.assign((size_t)n + 1, 0);
+  for (int i = 0; i < n; ++i) off[i + 1] = off[i] + summaries[i].n_positions;
+  const size_t total = off[n];
+  if (n + 1 > b->cap_offsets) {
+    cudaFree(b->d_offsets);
+    b->d_offsets = nullptr;
+    CK(cudaMalloc(&b->d_offsets, ((size_t)n + 1) * sizeof(uint32_t)));
+    b->cap_offsets = n + 1;
+  }
+  if (total > b->cap_dense) {
+    cudaFree(b->d_dense);
+    if (b->h_dense) cudaFreeHost(b->h_dense);
+    b->d_dense = nullptr; b->h_dense = nullptr;
+    CK(cudaMalloc(&b->d_dense, total * sizeof(ar_position_record)));
+    CK(cudaHostAlloc(&b->h_dense, total * sizeof(ar_position_record), cudaHostAllocDefault));
+    b->cap_dense = total;
+  }
+  if (total > 0) {
+    CK(cudaMemcpyAsync(b->d_offsets, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
+    compact_positions_kernel<<<(n + 7) / 8, 256, 0, b->stream>>>(b->d_positions, b->resident_stride, b->d_offsets, n, b->d_dense);
+    CK(cudaGetLastError());
+  }
+  b->launches += 1;
+  return AR_OK;
+}
+
 ar_status ar_selfplay_download(ar_engine* e, ar_game_summary* summaries, ar_position_record* positions,
                                int32_t positions_stride) {
   if (!e) return AR_ERR_INVALID_ARG;
   CK(cudaSetDevice(e->device));
-  int n = e->n_resident;
+  if (!e->cur->resident_valid) {
+    e->err = "no uploaded batch to download (a search or evaluator call reused the buffers)";
+    return AR_ERR_INVALID_ARG;
+  }
+  int n = e->cur->n_resident;
   if (n == 0) return AR_OK;
   if (!summaries || !positions) { e->err = "summaries/positions is NULL"; return AR_ERR_INVALID_ARG; }
   if (positions_stride < 1) { e->err = "positions_stride < 1"; return AR_ERR_INVALID_ARG; }
-  CK(cudaMemcpy(summaries, e->d_summaries, (size_t)n * sizeof(ar_game_summary), cudaMemcpyDeviceToHost));
-  for (int i = 0; i < n; ++i)
-    if ((int)summaries[i].n_positions > positions_stride) {
-      e->err = "positions_stride smaller than a game's length";
-      return AR_ERR_INVALID_ARG;
-    }
   // pack on device, one bulk copy into pinned staging, scatter into the caller's strided array
-  std::vector<uint32_t> off((size_t)n + 1, 0);
-  for (int i = 0; i < n; ++i) off[i + 1] = off[i] + summaries[i].n_positions;
+  std::vector<uint32_t> off;
+  ar_status ps = pack_records(e, summaries, positions_stride, off);
+  if (ps) return ps;
   const size_t total = off[n];
-  if (n + 1 > e->cap_offsets) {
-    cudaFree(e->d_offsets);
-    e->d_offsets = nullptr;
-    CK(cudaMalloc(&e->d_offsets, ((size_t)n + 1) * sizeof(uint32_t)));
-    e->cap_offsets = n + 1;
-  }
-  if (total > e->cap_dense) {
-    cudaFree(e->d_dense);
-    if (e->h_dense) cudaFreeHost(e->h_dense);
-    e->d_dense = nullptr; e->h_dense = nullptr;
-    CK(cudaMalloc(&e->d_dense, total * sizeof(ar_position_record)));
-    CK(cudaHostAlloc(&e->h_dense, total * sizeof(ar_position_record), cudaHostAllocDefault));
-    e->cap_dense = total;
-  }
   if (total > 0) {
-    CK(cudaMemcpyAsync(e->d_offsets, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
-    compact_positions_kernel<<<(n + 7) / 8, 256, 0, e->stream>>>(e->d_positions, e->resident_stride, e->d_offsets, n,
-                                                                 e->d_dense);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(e->h_dense, e->d_dense, total * sizeof(ar_position_record), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpyAsync(e->cur->h_dense, e->cur->d_dense, total * sizeof(ar_position_record), cudaMemcpyDeviceToHost, e->cur->stream));
+    CK(cudaStreamSynchronize(e->cur->stream));
   }
-  e->launches += 1;
-  e->d2h += (uint64_t)n * sizeof(ar_game_summary) + total * sizeof(ar_position_record);
+  e->cur->d2h += (uint64_t)n * sizeof(ar_game_summary) + total * sizeof(ar_position_record);
   // scatter into the caller's strided array, split over a few host threads
   auto finish = [&](int lo, int hi) {
     for (int i = lo; i < hi; ++i) {
       ar_position_record* dst = positions + (size_t)i * positions_stride;
       if (summaries[i].n_positions)
-        memcpy(dst, e->h_dense + off[i], (size_t)summaries[i].n_positions * sizeof(ar_position_record));
+        memcpy(dst, e->cur->h_dense + off[i], (size_t)summaries[i].n_positions * sizeof(ar_position_record));
     }
   };
   const int n_thr = n >= 4096 ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
@@ -1663,6 +1787,27 @@ ar_status ar_selfplay_download(ar_engine* e, ar_game_summary* summaries, ar_posi
   return AR_OK;
 }
 
+// The resident batch's records, packed, as DEVICE pointers (valid until the next call on this engine):
+// what a multi-GPU run hands to ncclGather / all_gather instead of bouncing records through the host.
+ar_status ar_selfplay_pack_device(ar_engine* e, ar_game_summary* summaries, const void** d_summaries,
+                                  const void** d_records, uint64_t* n_records) {
+  if (!e) return AR_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  if (!e->cur->resident_valid) { e->err = "no uploaded batch to pack"; return AR_ERR_INVALID_ARG; }
+  if (!summaries || !d_summaries || !d_records || !n_records) { e->err = "output is NULL"; return AR_ERR_INVALID_ARG; }
+  *d_summaries = e->cur->d_summaries;
+  *d_records = nullptr;
+  *n_records = 0;
+  if (e->cur->n_resident == 0) return AR_OK;
+  std::vector<uint32_t> off;
+  ar_status ps = pack_records(e, summaries, 0, off);
+  if (ps) return ps;
+  CK(cudaStreamSynchronize(e->cur->stream));
+  *d_records = e->cur->d_dense;
+  *n_records = off[e->cur->n_resident];
+  return AR_OK;
+}
+
 ar_status ar_selfplay_run(ar_engine* e, const ar_game_pod* games, int32_t n, const ar_search_cfg* cfg,
                           const uint64_t* seeds, ar_game_summary* summaries, ar_position_record* positions,
                           int32_t positions_stride, ar_progress* progress, ar_stats* stats) {
@@ -1671,7 +1816,7 @@ ar_status ar_selfplay_run(ar_engine* e, const ar_game_pod* games, int32_t n, con
   auto t0 = std::chrono::steady_clock::now();
   if (stats) memset(stats, 0, sizeof(*stats));
   if (progress) memset((void*)progress, 0, sizeof(*progress));
-  e->h2d = e->d2h = 0;
+  e->cur->h2d = e->cur->d2h = 0;
   ar_status s = validate_cfg(e, cfg);
   if (s) return s;
   s = ar_selfplay_upload(e, games, n, seeds);
@@ -1680,26 +1825,11 @@ ar_status ar_selfplay_run(ar_engine* e, const ar_game_pod* games, int32_t n, con
   if (s) return s;
   s = ar_selfplay_download(e, summaries, positions, positions_stride);
   if (s) return s;
-  if (stats) {  // SelfPlayStats::from_games, selfplay.rs:212-224
-    stats->min_turns = 0xffffffffu;
-    for (int i = 0; i < n; ++i) {
-      const ar_game_summary& g = summaries[i];
-      stats->total_games += 1;
-      stats->total_positions += g.n_positions;
-      stats->total_simulations += g.total_simulations;
-      stats->total_nn_evals += g.total_nn_evals;
-      stats->total_terminals += g.total_terminals;
-      stats->total_collisions += g.total_collisions;
-      stats->total_cheese_collected += g.final_p1_score + g.final_p2_score;
-      stats->total_cheese_available += g.cheese_available;
-      stats->min_turns = std::min(stats->min_turns, g.n_positions);
-      stats->max_turns = std::max(stats->max_turns, g.n_positions);
-      if (g.result == 1) stats->p1_wins++; else if (g.result == 2) stats->p2_wins++; else stats->draws++;
-    }
-    if (n == 0) stats->min_turns = 0;
+  if (stats) {
+    fill_game_stats(stats, summaries, n);
     stats->elapsed_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    stats->h2d_bytes = e->h2d;
-    stats->d2h_bytes = e->d2h;
+    stats->h2d_bytes = e->cur->h2d;
+    stats->d2h_bytes = e->cur->d2h;
   }
   return AR_OK;
 }
@@ -1719,9 +1849,9 @@ ar_status ar_encode_observations(ar_engine* e, const ar_game_pod* games, int32_t
     }
   float* d_obs = nullptr;
   CK(cudaMalloc(&d_obs, (size_t)n * dim * sizeof(float)));
-  cudaError_t ce = encode_f32(e->d_rows, n, e->d_games, dim, d_obs, e->stream);
-  if (ce == cudaSuccess) ce = cudaMemcpyAsync(obs, d_obs, (size_t)n * dim * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
-  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+  cudaError_t ce = encode_f32(e->d_rows, n, e->cur->d_games, dim, d_obs, e->cur->stream);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(obs, d_obs, (size_t)n * dim * sizeof(float), cudaMemcpyDeviceToHost, e->cur->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->cur->stream);
   cudaFree(d_obs);
   if (ce != cudaSuccess) { e->err = std::string("encode: ") + cudaGetErrorString(ce); return AR_ERR_CUDA; }
   return AR_OK;
@@ -1741,15 +1871,15 @@ ar_status ar_nn_forward(ar_engine* e, const ar_game_pod* games, int32_t n, float
       e->err = "game " + std::to_string(i) + " does not match the evaluator's board size";
       return AR_ERR_INVALID_ARG;
     }
-  CK(cudaMemsetAsync(e->d_error, 0, sizeof(int), e->stream));
+  CK(cudaMemsetAsync(e->cur->d_error, 0, sizeof(int), e->cur->stream));
   s = ensure_maze_table(e, n);
   if (s) return s;
-  CK(e->eval->forward(e->d_rows, nullptr, n, e->d_games, e->d_maze_tab, e->d_nn_out, e->d_error, e->stream));
+  CK(e->eval->forward(e->d_rows, nullptr, n, e->cur->d_games, e->d_maze_tab, e->d_nn_out, e->cur->d_error, e->cur->stream));
   std::vector<float> out((size_t)n * 12);
-  CK(cudaMemcpyAsync(out.data(), e->d_nn_out, out.size() * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+  CK(cudaMemcpyAsync(out.data(), e->d_nn_out, out.size() * sizeof(float), cudaMemcpyDeviceToHost, e->cur->stream));
   int herr = 0;
-  CK(cudaMemcpyAsync(&herr, e->d_error, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaMemcpyAsync(&herr, e->cur->d_error, sizeof(int), cudaMemcpyDeviceToHost, e->cur->stream));
+  CK(cudaStreamSynchronize(e->cur->stream));
   if (herr) { e->err = "evaluator produced a non-finite value"; return (ar_status)herr; }
   for (int i = 0; i < n; ++i) {
     memcpy(policy_p1 + i * 5, &out[(size_t)i * 12], 20);
@@ -1757,6 +1887,225 @@ ar_status ar_nn_forward(ar_engine* e, const ar_game_pod* games, int32_t n, float
     value_p1[i] = out[(size_t)i * 12 + 10];
     value_p2[i] = out[(size_t)i * 12 + 11];
   }
+  return AR_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+// Streaming self-play (continuous game feed): several batches in flight on one engine.
+// Every batch is one persistent launch of selfplay_uniform_kernel on its own stream; launches share
+// the engine's tree slots through the device-side group bitmap, so the next batch's blocks start as
+// the previous batch's blocks finish their last (longest) games — throughput no longer depends on the
+// number of games per call (a lone batch ends with a tail of long games running alone).
+// Uniform-prior warp engine only.
+// -----------------------------------------------------------------------------------------
+static ar_status stream_buf(ar_engine* e, int32_t buffer, BatchBuf** out) {
+  if (!e) return AR_ERR_INVALID_ARG;
+  if (buffer < 0 || buffer >= (int)e->sbufs.size()) { e->err = "no such stream buffer (ar_stream_open)"; return AR_ERR_INVALID_ARG; }
+  *out = e->sbufs[buffer];
+  return AR_OK;
+}
+
+ar_status ar_stream_open(ar_engine* e, int32_t n_buffers, int32_t max_games, int32_t positions_stride) {
+  if (!e) return AR_ERR_INVALID_ARG;
+  CK(cudaSetDevice(e->device));
+  if (n_buffers < 1 || n_buffers > 8 || max_games < 1 || positions_stride < 1) { e->err = "bad stream shape"; return AR_ERR_INVALID_ARG; }
+  if (e->arch != AR_ARCH_UNIFORM || e->cfg.tree_engine != AR_TREE_WARP) {
+    e->err = "streaming is implemented for the uniform-prior warp engine";
+    return AR_ERR_UNSUPPORTED;
+  }
+  ar_stream_close(e);
+  for (int i = 0; i < n_buffers; ++i) {
+    BatchBuf* b = new BatchBuf();
+    e->sbufs.push_back(b);
+    CK(batch_init(*b));
+    CK(cudaMalloc(&b->d_games, (size_t)max_games * sizeof(ar_game_pod)));
+    CK(cudaMalloc(&b->d_seeds, (size_t)max_games * sizeof(uint64_t)));
+    CK(cudaMalloc(&b->d_summaries, (size_t)max_games * sizeof(ar_game_summary)));
+    CK(cudaMalloc(&b->d_positions, (size_t)max_games * positions_stride * sizeof(ar_position_record)));
+    CK(cudaHostAlloc(&b->h_games_pinned, (size_t)max_games * sizeof(ar_game_pod), cudaHostAllocDefault));
+    CK(cudaHostAlloc(&b->h_seeds_pinned, (size_t)max_games * sizeof(uint64_t), cudaHostAllocDefault));
+    b->cap_games = max_games;
+    b->cap_stride = positions_stride;
+  }
+  if (!e->ev_base) CK(cudaEventCreate(&e->ev_base));
+  CK(cudaEventRecord(e->ev_base, e->main.stream));
+  CK(cudaStreamSynchronize(e->main.stream));
+  if (!e->d_slot_bitmap) {
+    CK(cudaMalloc(&e->d_slot_bitmap, (size_t)((e->n_slots / 4 + 31) / 32 + 1) * sizeof(uint32_t)));
+    CK(cudaMemset(e->d_slot_bitmap, 0, (size_t)((e->n_slots / 4 + 31) / 32 + 1) * sizeof(uint32_t)));
+  }
+  return AR_OK;
+}
+
+void ar_stream_close(ar_engine* e) {
+  if (!e) return;
+  for (BatchBuf* b : e->sbufs) {
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    batch_free(*b);
+    delete b;
+  }
+  e->sbufs.clear();
+  e->cur = &e->main;
+}
+
+// Launch the resident batch of `buffer` (asynchronous).
+ar_status ar_stream_launch(ar_engine* e, int32_t buffer, const ar_search_cfg* cfg) {
+  BatchBuf* b = nullptr;
+  ar_status s = stream_buf(e, buffer, &b);
+  if (s) return s;
+  CK(cudaSetDevice(e->device));
+  if (b->in_flight) { e->err = "stream buffer is still in flight (ar_stream_wait / ar_stream_collect)"; return AR_ERR_INVALID_ARG; }
+  if (!b->resident_valid) { e->err = "stream buffer holds no batch"; return AR_ERR_INVALID_ARG; }
+  s = validate_cfg(e, cfg);
+  if (s) return s;
+  s = ensure_coll_table(e, *cfg);
+  if (s) return s;
+  s = ensure_nn_pools(e);
+  if (s) return s;
+  if (e->n_slots < 4) { e->err = "streaming needs at least 4 resident trees"; return AR_ERR_INVALID_ARG; }
+  e->cur = b;
+  RunParams p = make_params(e, cfg);
+  e->cur = &e->main;
+  p.pools = e->pools; p.pool_nodes = e->pool_nodes; p.path_bufs = e->path_bufs; p.remaps = e->remaps;
+  p.games = b->d_games; p.seeds = b->d_seeds; p.n_games = b->n_resident;
+  p.summaries = b->d_summaries; p.positions = b->d_positions; p.pos_stride = b->resident_stride;
+  p.search_only = 0;
+  p.slot_bitmap = e->d_slot_bitmap;
+  p.n_groups = (int)e->n_slots / 4;
+  p.n_slots = p.n_groups * 4;
+  p.progress = nullptr;
+  b->launches = 0;
+  b->t_submit = std::chrono::steady_clock::now();
+  CK(cudaMemsetAsync(b->d_next, 0, sizeof(unsigned int), b->stream));
+  CK(cudaMemsetAsync(b->d_counters, 0, 8 * sizeof(unsigned long long), b->stream));
+  CK(cudaMemsetAsync(b->d_error, 0, sizeof(int), b->stream));
+  CK(cudaEventRecord(b->ev0, b->stream));
+  if (b->n_resident > 0) {
+    const size_t smem = 4 * warp_smem_bytes(e->max_depth, e->batch_cap);
+    const int blocks = std::min(p.n_groups, (b->n_resident + 3) / 4);
+    selfplay_uniform_kernel<<<blocks, 128, smem, b->stream>>>(p);
+    CK(cudaGetLastError());
+    b->launches = 1;
+  }
+  CK(cudaEventRecord(b->ev1, b->stream));
+  b->in_flight = true;
+  return AR_OK;
+}
+
+// Copy a batch into `buffer` from host memory (asynchronous, through pinned staging) and launch it.
+ar_status ar_stream_submit(ar_engine* e, int32_t buffer, const ar_game_pod* games, int32_t n,
+                           const ar_search_cfg* cfg, const uint64_t* seeds) {
+  BatchBuf* b = nullptr;
+  ar_status s = stream_buf(e, buffer, &b);
+  if (s) return s;
+  CK(cudaSetDevice(e->device));
+  if (b->in_flight) { e->err = "stream buffer is still in flight (ar_stream_collect)"; return AR_ERR_INVALID_ARG; }
+  s = validate_games(e, games, n);
+  if (s) return s;
+  if (n > b->cap_games) { e->err = "batch larger than the stream's max_games"; return AR_ERR_INVALID_ARG; }
+  if (n > 0 && !seeds) { e->err = "seeds is NULL"; return AR_ERR_INVALID_ARG; }
+  for (int i = 0; i < n; ++i)
+    if (games[i].max_turns > b->cap_stride) { e->err = "a game's max_turns exceeds the stream's positions_stride"; return AR_ERR_INVALID_ARG; }
+  if (n > 0) {
+    memcpy(b->h_games_pinned, games, (size_t)n * sizeof(ar_game_pod));
+    memcpy(b->h_seeds_pinned, seeds, (size_t)n * sizeof(uint64_t));
+    CK(cudaMemcpyAsync(b->d_games, b->h_games_pinned, (size_t)n * sizeof(ar_game_pod), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaMemcpyAsync(b->d_seeds, b->h_seeds_pinned, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice, b->stream));
+  }
+  b->n_resident = n;
+  b->resident_stride = b->cap_stride;
+  b->resident_valid = true;
+  b->h2d = (uint64_t)n * (sizeof(ar_game_pod) + sizeof(uint64_t));
+  b->d2h = 0;
+  if (!cfg) return AR_OK;  // upload only: ar_stream_launch plays it
+  return ar_stream_launch(e, buffer, cfg);
+}
+
+// Wait for the launch of `buffer`; stats (optional) carry device time and the roofline counters.
+ar_status ar_stream_wait(ar_engine* e, int32_t buffer, ar_stats* stats) {
+  BatchBuf* b = nullptr;
+  ar_status s = stream_buf(e, buffer, &b);
+  if (s) return s;
+  CK(cudaSetDevice(e->device));
+  if (!b->in_flight) { e->err = "stream buffer has no launch in flight"; return AR_ERR_INVALID_ARG; }
+  CK(cudaStreamSynchronize(b->stream));
+  b->in_flight = false;
+  int herr = 0;
+  CK(cudaMemcpy(&herr, b->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+  if (herr != 0) {
+    e->err = "device reported status " + std::to_string(herr) + " (node pool / depth stack exhausted: raise pool_nodes or max_turns)";
+    return (ar_status)herr;
+  }
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+    unsigned long long c[8] = {0};
+    CK(cudaMemcpy(c, b->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+    stats->device_ms = ms;
+    stats->path_nodes = c[0];
+    stats->new_nodes = c[1];
+    stats->total_nn_evals = c[2];
+    stats->total_terminals = c[3];
+    stats->total_positions = c[4];
+    stats->total_simulations = c[5];
+    stats->total_games = (uint32_t)b->n_resident;
+    stats->kernel_launches = b->launches;
+    stats->elapsed_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - b->t_submit).count();
+  }
+  return AR_OK;
+}
+
+// Wait for `buffer`, then download its records into host memory.
+ar_status ar_stream_collect(ar_engine* e, int32_t buffer, ar_game_summary* summaries, ar_position_record* positions,
+                            int32_t positions_stride, ar_stats* stats) {
+  BatchBuf* b = nullptr;
+  ar_status s = stream_buf(e, buffer, &b);
+  if (s) return s;
+  ar_stats local{};
+  s = ar_stream_wait(e, buffer, &local);
+  if (s) return s;
+  e->cur = b;
+  s = ar_selfplay_download(e, summaries, positions, positions_stride);
+  e->cur = &e->main;
+  if (s) return s;
+  if (stats) {
+    *stats = local;
+    fill_game_stats(stats, summaries, b->n_resident);
+    stats->kernel_launches = b->launches;
+    stats->h2d_bytes = b->h2d;
+    stats->d2h_bytes = b->d2h;
+    stats->elapsed_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - b->t_submit).count();
+  }
+  return AR_OK;
+}
+
+// Start and end of the last completed launch of `buffer` on the device clock, in ms since ar_stream_open
+// (valid after ar_stream_wait / ar_stream_collect, until the buffer is launched again).
+ar_status ar_stream_times(ar_engine* e, int32_t buffer, double* start_ms, double* end_ms) {
+  BatchBuf* b = nullptr;
+  ar_status s = stream_buf(e, buffer, &b);
+  if (s) return s;
+  if (!start_ms || !end_ms || b->in_flight) { e->err = "ar_stream_times: buffer in flight or NULL output"; return AR_ERR_INVALID_ARG; }
+  float f0 = 0, f1 = 0;
+  CK(cudaEventElapsedTime(&f0, e->ev_base, b->ev0));
+  CK(cudaEventElapsedTime(&f1, e->ev_base, b->ev1));
+  *start_ms = f0;
+  *end_ms = f1;
+  return AR_OK;
+}
+
+// Device time from the start of buffer `first`'s launch to the end of buffer `last`'s (both complete).
+ar_status ar_stream_elapsed_ms(ar_engine* e, int32_t first, int32_t last, double* ms) {
+  BatchBuf *a = nullptr, *b = nullptr;
+  ar_status s = stream_buf(e, first, &a);
+  if (s) return s;
+  s = stream_buf(e, last, &b);
+  if (s) return s;
+  if (!ms) return AR_ERR_INVALID_ARG;
+  float f = 0;
+  CK(cudaEventElapsedTime(&f, a->ev0, b->ev1));
+  *ms = f;
   return AR_OK;
 }
 

@@ -141,6 +141,56 @@ class Engine:
         self._check(self._lib.ar_selfplay_download(self._h, summaries, positions, stride), "ar_selfplay_download")
         return summaries, positions
 
+    def selfplay_pack_device(self, n: int):
+        """Packed records of the resident batch as device memory: `(summaries_host, d_summaries, d_records,
+        n_records)`; the device pointers are ints (see `parallel.device_bytes`)."""
+        summaries = (N.GameSummary * max(n, 1))()
+        ds, dr, nr = C.c_void_p(), C.c_void_p(), C.c_uint64(0)
+        self._check(self._lib.ar_selfplay_pack_device(self._h, summaries, C.byref(ds), C.byref(dr), C.byref(nr)),
+                    "ar_selfplay_pack_device")
+        return summaries, ds.value or 0, dr.value or 0, int(nr.value)
+
+    # --- streaming self-play (continuous game feed, ar_stream_*) -------------------------------
+    def stream_open(self, n_buffers: int, max_games: int, stride: int) -> None:
+        self._check(self._lib.ar_stream_open(self._h, n_buffers, max_games, stride), "ar_stream_open")
+
+    def stream_close(self) -> None:
+        self._lib.ar_stream_close(self._h)
+
+    def stream_submit(self, buffer: int, pods, cfg: N.SearchCfg | None, seeds) -> None:
+        """Upload a batch into `buffer` and launch it; `cfg=None` uploads only (`stream_launch` plays it).
+        `seeds` may be a ready `c_uint64` array."""
+        n = len(pods)
+        sd = seeds if isinstance(seeds, C.Array) else (C.c_uint64 * max(n, 1))(*[int(s) & ((1 << 64) - 1) for s in seeds])
+        self._check(self._lib.ar_stream_submit(self._h, buffer, pods, n, C.byref(cfg) if cfg is not None else None, sd),
+                    "ar_stream_submit")
+
+    def stream_collect(self, buffer: int, n: int, stride: int):
+        summaries = (N.GameSummary * max(n, 1))()
+        positions = self._record_array(max(n * stride, 1))
+        stats = N.Stats()
+        self._check(self._lib.ar_stream_collect(self._h, buffer, summaries, positions, stride, C.byref(stats)),
+                    "ar_stream_collect")
+        return summaries, positions, stride, stats
+
+    def stream_launch(self, buffer: int, cfg: N.SearchCfg) -> None:
+        self._check(self._lib.ar_stream_launch(self._h, buffer, C.byref(cfg)), "ar_stream_launch")
+
+    def stream_wait(self, buffer: int) -> N.Stats:
+        stats = N.Stats()
+        self._check(self._lib.ar_stream_wait(self._h, buffer, C.byref(stats)), "ar_stream_wait")
+        return stats
+
+    def stream_times(self, buffer: int) -> tuple[float, float]:
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        self._check(self._lib.ar_stream_times(self._h, buffer, C.byref(a), C.byref(b)), "ar_stream_times")
+        return a.value, b.value
+
+    def stream_elapsed_ms(self, first: int, last: int) -> float:
+        ms = C.c_double(0.0)
+        self._check(self._lib.ar_stream_elapsed_ms(self._h, first, last, C.byref(ms)), "ar_stream_elapsed_ms")
+        return ms.value
+
     # --- evaluator entry points ------------------------------------------------------------
     def encode(self, pods) -> np.ndarray:
         n = len(pods)

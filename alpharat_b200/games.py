@@ -258,18 +258,24 @@ def make_games(
     mud_density: float = 0.1,
     maze_symmetric: bool = True,
     first_index: int = 0,
+    layout_seed: int | None = None,
 ) -> list[GameSpec]:
     """Generator behind `cuda_self_play` (same axes as `make_games`, bindings.rs:489-533):
     maze_type open / classic (wall 0.7, mud 0.1, symmetric) / random; positions corners / random
     (P2 is the 180-degree mirror of P1 when the cheese is symmetric); random cheese.
-    One SplitMix64 stream per game, keyed by the game index."""
+    One SplitMix64 stream per game.  `layout_seed=None` keys the stream by the game index alone
+    (reproducible: tests, benchmarks); a run seed is mixed in otherwise, so that successive sampling
+    runs see different boards, as the reference's `config.create(None)` does (bindings.rs:529-532)."""
     if maze_type not in ("open", "classic", "random"):
         raise ValueError(f"unknown maze_type: {maze_type!r}")
     if positions not in ("corners", "random"):
         raise ValueError(f"unknown positions: {positions!r}")
     out = []
     for i in range(num_games):
-        rng = SplitMix64(first_index + i)
+        key = first_index + i
+        if layout_seed is not None:  # one SplitMix64 output of the run seed, xor-folded with the index
+            key = (SplitMix64(layout_seed & ((1 << 64) - 1)).next() ^ (key * 0x9E3779B97F4A7C15)) & ((1 << 64) - 1)
+        rng = SplitMix64(key)
         walls, mud = [], []
         if maze_type == "classic":
             walls, mud = random_maze(width, height, 0.7, 0.1, 3, True, rng)

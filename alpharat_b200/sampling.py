@@ -18,9 +18,8 @@ is also how the tests drive this function without the reference installed).
 from __future__ import annotations
 
 import logging
-import threading
 import time
-from dataclasses import dataclass
+from dataclasses import dataclass, fields
 from pathlib import Path
 from typing import Any
 
@@ -171,61 +170,49 @@ def run_cuda_sampling(
         device=resolve_sampling_device(device),
         cache_size=cache_size,
     )
-    stats = _run_with_progress(self_play_fn, kwargs, num_games) if verbose else self_play_fn(**kwargs)
+    stats = _play_reporting(self_play_fn, kwargs, num_games) if verbose else self_play_fn(**kwargs)
 
     exp.register_batch(group=group, batch_uuid=batch_uuid, mcts_config=mcts, game=game, checkpoint_path=checkpoint)
 
-    metrics = CudaSamplingMetrics(
-        total_games=stats.total_games,
-        total_positions=stats.total_positions,
-        total_simulations=stats.total_simulations,
-        elapsed_seconds=stats.elapsed_secs,
-        p1_wins=stats.p1_wins,
-        p2_wins=stats.p2_wins,
-        draws=stats.draws,
-        total_cheese_collected=stats.total_cheese_collected,
-        total_cheese_available=stats.total_cheese_available,
-        min_turns=stats.min_turns,
-        max_turns=stats.max_turns,
-        total_nn_evals=stats.total_nn_evals,
-        total_terminals=stats.total_terminals,
-        total_collisions=stats.total_collisions,
-        cache_hits=stats.cache_hits,
-        cache_misses=stats.cache_misses,
-    )
-    logger.info(
-        "CUDA self-play complete: %d games, %d positions, %.0f sims/s (%.0f nn_evals/s, %.0f%% nn, %.1fs)",
-        metrics.total_games, metrics.total_positions, metrics.simulations_per_second,
-        metrics.nn_evals_per_second, metrics.nn_eval_fraction * 100, metrics.elapsed_seconds,
-    )
+    # every metric is a same-named attribute of the stats object except the elapsed time
+    renamed = {"elapsed_seconds": "elapsed_secs"}
+    metrics = CudaSamplingMetrics(**{f.name: getattr(stats, renamed.get(f.name, f.name))
+                                     for f in fields(CudaSamplingMetrics)})
+    logger.info("backend cuda: %s", _summary_line(metrics))
     return Path(batch_dir), metrics
 
 
-def _run_with_progress(self_play_fn: Any, kwargs: dict[str, Any], num_games: int) -> Any:
-    """Play in a background thread and poll the live counters (rust_sampling.py:299-338)."""
-    from tqdm import tqdm
+def _summary_line(m: CudaSamplingMetrics) -> str:
+    parts = [f"{m.total_games} games", f"{m.total_positions} positions", f"{m.elapsed_seconds:.1f} s",
+             f"{m.simulations_per_second:,.0f} sims/s", f"{m.games_per_second * 3600:,.0f} games/h",
+             f"nn {m.nn_eval_fraction:.0%} / terminal {m.terminal_fraction:.0%} / collision {m.collision_fraction:.1%}"]
+    if m.cache_hits + m.cache_misses:
+        parts.append(f"cache hit {m.cache_hit_rate:.0%}")
+    return ", ".join(parts)
+
+
+def _play_reporting(self_play_fn: Any, kwargs: dict[str, Any], num_games: int, period_s: float = 2.0) -> Any:
+    """Run the blocking self-play call on a worker and report the engine's live counters while it runs.
+
+    The engine keeps `SelfPlayProgress` up to date from the device (host-mapped counters); this thread
+    only reads it.  One log line per `period_s` with games done, rate and an ETA — no progress-bar
+    dependency, so it behaves the same in a terminal, a notebook and a job log."""
+    from concurrent.futures import ThreadPoolExecutor
 
     progress = SelfPlayProgress()
-    kwargs["progress"] = progress
-    result: list[Any] = []
-    error: list[BaseException] = []
-
-    def _worker() -> None:
-        try:
-            result.append(self_play_fn(**kwargs))
-        except BaseException as e:  # re-raised on the caller's thread
-            error.append(e)
-
-    thread = threading.Thread(target=_worker, daemon=True)
-    thread.start()
-    with tqdm(total=num_games, desc="CUDA self-play", unit="game") as pbar:
-        while thread.is_alive():
-            pbar.n = progress.games_completed
-            pbar.refresh()
-            time.sleep(0.2)
-        pbar.n = progress.games_completed
-        pbar.refresh()
-    thread.join()
-    if error:
-        raise error[0]
-    return result[0]
+    t0 = time.monotonic()
+    with ThreadPoolExecutor(max_workers=1, thread_name_prefix="cuda-self-play") as pool:
+        fut = pool.submit(self_play_fn, **dict(kwargs, progress=progress))
+        next_report = t0 + period_s
+        while not fut.done():
+            time.sleep(0.05)
+            now = time.monotonic()
+            if now < next_report:
+                continue
+            next_report = now + period_s
+            done = progress.games_completed
+            rate = done / (now - t0)
+            eta = (num_games - done) / rate if rate > 0 else float("inf")
+            logger.info("self-play %d/%d games, %.0f games/s, %d positions, eta %.0f s", done, num_games, rate,
+                        progress.positions_completed, eta)
+        return fut.result()  # re-raises the worker's exception, if any

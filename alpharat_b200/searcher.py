@@ -59,20 +59,39 @@ class CudaSearcher:
                                collision_scaling_end=collision_scaling_end,
                                collision_scaling_power=collision_scaling_power)
         self._seed = seed
-        pn = pool_nodes or min(65535, simulations + 64)
-        self._engine = Engine(device=device, concurrent_games=concurrent, pool_nodes=max(pn, 64),
-                              max_turns=max_turns, max_batch_size=max(batch_size, 1),
-                              max_simulations=simulations)
-        if checkpoint is not None:
+        self._simulations = simulations
+        self._batch_size = max(batch_size, 1)
+        self._device, self._pool_nodes, self._concurrent = device, pool_nodes, concurrent
+        self._checkpoint = checkpoint
+        self._engine: Engine | None = None
+        self._engine_turns = 0
+        self._ensure_engine(max_turns)
+
+    # The engine's depth stack is sized by max_turns (hard limit of this build: 250 turns); it is rebuilt
+    # when a game with a larger max_turns arrives, so any PyRat game the reference Searcher accepts is
+    # accepted here as long as max_turns <= 250.
+    def _ensure_engine(self, max_turns: int) -> None:
+        if self._engine is not None and max_turns <= self._engine_turns:
+            return
+        if self._engine is not None:
+            self._engine.close()
+        turns = min(250, max(max_turns, 1))
+        pn = self._pool_nodes or (self._simulations + 64)  # a fresh tree per call: at most `simulations` + 1 nodes
+        self._engine = Engine(device=self._device, concurrent_games=self._concurrent, pool_nodes=max(pn, 64),
+                              max_turns=turns, max_batch_size=self._batch_size,
+                              max_simulations=self._simulations)
+        self._engine_turns = turns
+        if self._checkpoint is not None:
             from .weights import load_checkpoint_into
 
-            load_checkpoint_into(self._engine, checkpoint)
+            load_checkpoint_into(self._engine, self._checkpoint)
 
     def _pod(self, game: Any) -> N.GamePod:
         return game if isinstance(game, N.GamePod) else pod_from_pyrat(game)
 
     def search_many(self, games: list[Any], seeds: list[int] | None = None) -> list[N.SearchResultPod]:
         pods = (N.GamePod * len(games))(*[self._pod(g) for g in games])
+        self._ensure_engine(max([p.max_turns for p in pods] + [1]))
         if seeds is None:
             base = self._seed
             seeds = [base if base is not None else secrets.randbits(64) for _ in games]

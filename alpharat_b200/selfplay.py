@@ -142,10 +142,12 @@ def cuda_self_play(
     # --- extensions ---
     games: Sequence[GameSpec] | None = None,
     seed: int | None = None,
+    first_index: int = 0,  # index of the first game in a larger run (multi-GPU shards)
     checkpoint: str | None = None,
     concurrent_games: int = 4096,
     pool_nodes: int = 0,
     engine: Engine | None = None,
+    tree_engine: str = "warp",
     return_records: bool = False,
 ):
     """Play `num_games` games on the GPU and write bundles; returns `SelfPlayStats`."""
@@ -153,10 +155,14 @@ def cuda_self_play(
         raise ValueError("onnx_model_path is not used by backend cuda: pass checkpoint=<.pt>")
     if cache_size < 0:
         raise ValueError("cache_size must be >= 0")
+    # Run seed: explicit `seed=` makes layouts and search reproducible; otherwise it comes from entropy, so
+    # successive sampling runs (iterate: sample, train, sample) never replay the same boards — the reference
+    # creates every game from entropy (config.create(None), bindings.rs:529-532).
+    base_seed = seed if seed is not None else secrets.randbits(63)
     specs = list(games) if games is not None else make_games(
         num_games, width=width, height=height, cheese_count=cheese_count, max_turns=max_turns,
         cheese_symmetric=cheese_symmetric, maze_type=maze_type, positions=positions, wall_density=wall_density,
-        mud_density=mud_density, maze_symmetric=maze_symmetric)
+        mud_density=mud_density, maze_symmetric=maze_symmetric, first_index=first_index, layout_seed=base_seed)
     if games is not None and len(specs) != num_games:
         raise ValueError("len(games) != num_games")
     cfg = search_cfg(simulations=simulations, batch_size=batch_size, c_puct=c_puct,
@@ -164,15 +170,14 @@ def cuda_self_play(
                      noise_concentration=noise_concentration, collision_limit_min=collision_limit_min,
                      collision_limit_max=collision_limit_max, collision_scaling_start=collision_scaling_start,
                      collision_scaling_end=collision_scaling_end, collision_scaling_power=collision_scaling_power)
-    base_seed = seed if seed is not None else secrets.randbits(63)
-    seeds = [(base_seed + i) & ((1 << 64) - 1) for i in range(len(specs))]
+    seeds = [(base_seed + first_index + i) & ((1 << 64) - 1) for i in range(len(specs))]
     dev = resolve_sampling_device(device)
     own = engine is None
     if own:
         mt = max([s.max_turns for s in specs] + [1])
         engine = Engine(device=dev, concurrent_games=max(1, min(concurrent_games, max(len(specs), 1))),
                         pool_nodes=pool_nodes, max_turns=mt, max_batch_size=batch_size,
-                        max_simulations=simulations)
+                        max_simulations=simulations, tree_engine=tree_engine)
     try:
         if checkpoint is not None:
             from .weights import load_checkpoint_into

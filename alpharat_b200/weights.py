@@ -39,5 +39,7 @@ def load_checkpoint_into(engine, checkpoint_path: str) -> None:
     ck = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
     cfg = ck.get("config", {})
     model_cfg = cfg.get("model", {}) if isinstance(cfg, dict) else {}
-    arch = model_cfg.get("architecture", "mlp") if isinstance(model_cfg, dict) else getattr(model_cfg, "architecture", "mlp")
+    arch = model_cfg.get("architecture") if isinstance(model_cfg, dict) else getattr(model_cfg, "architecture", None)
+    if arch is None:  # the reference loader refuses too (alpharat/config/checkpoint.py:78-82)
+        raise ValueError(f"checkpoint {checkpoint_path!r} has no config.model.architecture discriminator")
     load_state_dict_into(engine, arch, int(ck["width"]), int(ck["height"]), ck["model_state_dict"])

@@ -216,6 +216,36 @@ ar_status ar_selfplay_run_resident(ar_engine* e, const ar_search_cfg* cfg, ar_st
 ar_status ar_selfplay_download(ar_engine* e, ar_game_summary* summaries,
                                ar_position_record* positions, int32_t positions_stride);
 
+/* The resident batch's records packed on the DEVICE (game-major, n_positions records per game) and its
+ * summaries: device pointers, valid until the next call on this engine.  For device-to-device gathers of
+ * recorded batches across GPUs (the aggregation of run_self_play, selfplay.rs:657-703, without a host
+ * bounce).  `summaries` (host, n entries) receives the summaries too: game lengths give the offsets. */
+ar_status ar_selfplay_pack_device(ar_engine* e, ar_game_summary* summaries, const void** d_summaries,
+                                  const void** d_records, uint64_t* n_records);
+
+/* Streaming self-play (continuous game feed).  The reference's worker pool never idles between batches:
+ * threads keep claiming game indices until the run is over (game_worker_loop, selfplay.rs:609-650,
+ * run_self_play_to_disk 706-808).  A lone GPU batch instead ends with a tail in which its last, longest
+ * games run alone; with several batches in flight the next batch's blocks take over the SMs as the previous
+ * batch's blocks finish, so throughput does not depend on the batch size.  `n_buffers` batches of up to
+ * `max_games` games can be in flight; submit / collect a buffer in turn.  Uniform-prior AR_TREE_WARP only.
+ *   ar_stream_submit   host games + seeds -> pinned staging -> device (async) and launch (async)
+ *   ar_stream_collect  wait for that buffer, download its records (same layout as ar_selfplay_run)
+ *   ar_stream_launch / ar_stream_wait   re-run a buffer whose inputs are already resident (kernel-only timing)
+ *   ar_stream_submit with cfg == NULL   upload only
+ *   ar_stream_times    start / end of a buffer's last completed launch on the device clock (ms since open)
+ *   ar_stream_elapsed_ms   device time from the start of buffer `first`'s launch to the end of `last`'s */
+ar_status ar_stream_open(ar_engine* e, int32_t n_buffers, int32_t max_games, int32_t positions_stride);
+void ar_stream_close(ar_engine* e);
+ar_status ar_stream_submit(ar_engine* e, int32_t buffer, const ar_game_pod* games, int32_t n,
+                           const ar_search_cfg* cfg, const uint64_t* seeds);
+ar_status ar_stream_collect(ar_engine* e, int32_t buffer, ar_game_summary* summaries,
+                            ar_position_record* positions, int32_t positions_stride, ar_stats* stats);
+ar_status ar_stream_launch(ar_engine* e, int32_t buffer, const ar_search_cfg* cfg);
+ar_status ar_stream_wait(ar_engine* e, int32_t buffer, ar_stats* stats);
+ar_status ar_stream_times(ar_engine* e, int32_t buffer, double* start_ms, double* end_ms);
+ar_status ar_stream_elapsed_ms(ar_engine* e, int32_t first, int32_t last, double* ms);
+
 /* FlatEncoder on device: obs is n * (7*w*h+6) f32, host memory. */
 ar_status ar_encode_observations(ar_engine* e, const ar_game_pod* games, int32_t n, float* obs);
 

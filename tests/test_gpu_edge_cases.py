@@ -130,7 +130,7 @@ def test_run_cuda_sampling_writes_a_registered_batch(oracle, tmp_path):
     assert len(mgr.registered) == 1 and m.total_games == 9
     files = sorted((batch_dir / "games").glob("bundle_*.npz"))
     assert len(files) == 3
-    specs = make_games(9, width=5, height=5, cheese_count=5, max_turns=30)
+    specs = make_games(9, width=5, height=5, cheese_count=5, max_turns=30, layout_seed=5)  # the run seed keys the boards
     cfg = search_cfg(simulations=60, batch_size=8)
     summ, pos, stride, st = oracle_selfplay(oracle, pods_array(specs), cfg, [5 + i for i in range(9)])
     assert (m.total_positions, m.total_simulations, m.p1_wins, m.p2_wins, m.draws) == (
@@ -150,3 +150,35 @@ def test_run_cuda_sampling_writes_a_registered_batch(oracle, tmp_path):
             vis = tuple(tuple(float(v) for v in row) for row in z["visit_counts_p1"][b:e])
             got[(acts, vis)] = got.get((acts, vis), 0) + 1
     assert got == want
+
+
+def test_streaming_batches_match_blocking_runs(oracle):
+    """ar_stream_*: three batches in flight through two buffers give, game for game, the records of the
+    blocking call and of the oracle (launches overlap on the device and share the tree slots)."""
+    from conftest import oracle_selfplay
+    from test_gpu_parity_uniform import compare_selfplay
+
+    n = 96
+    cfg = search_cfg(simulations=300, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103)
+    batches = []
+    for b in range(3):
+        specs = make_games(n, width=7, height=7, cheese_count=10, max_turns=50, first_index=7000 + b * n)
+        batches.append((pods_array(specs), [900 + b * n + i for i in range(n)]))
+    with Engine(concurrent_games=64, max_turns=50, max_batch_size=16, max_simulations=300) as eng:
+        eng.stream_open(2, n, 50)
+        eng.stream_submit(0, batches[0][0], cfg, batches[0][1])
+        eng.stream_submit(1, batches[1][0], cfg, batches[1][1])
+        got = [eng.stream_collect(0, n, 50)]
+        eng.stream_submit(0, batches[2][0], cfg, batches[2][1])
+        got.append(eng.stream_collect(1, n, 50))
+        got.append(eng.stream_collect(0, n, 50))
+        assert eng.stream_elapsed_ms(1, 0) > 0.0
+        with pytest.raises(ValueError):
+            eng.stream_collect(0, n, 50)  # nothing in flight
+        eng.stream_close()
+        blocking = eng.selfplay(batches[1][0], cfg, batches[1][1])
+    for b in range(3):
+        cpu = oracle_selfplay(oracle, batches[b][0], cfg, batches[b][1])
+        compare_selfplay(got[b], cpu, n)
+        assert got[b][3].total_games == n and got[b][3].path_nodes == cpu[3].path_nodes
+    compare_selfplay(got[1], blocking, n)
