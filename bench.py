@@ -210,11 +210,12 @@ def nn_runs():
     return {
         "mlp": dict(config="3: 7x7_rust_tuned + MLP(hidden 256), 16384 resident trees", arch=N.AR_ARCH_MLP,
                     sd=lambda: make_mlp_state_dict(0, 349), conc=16384, n=16384, sims=1897, fpu=0.459, fk=0.103),
+        # config 4 runs are short (1024 games through at most 4096 trees): bounded bench time
         "symmetric": dict(config="4: 7x7_rust_strong + SymmetricMLP(hidden 256), 4096 resident trees",
-                          arch=N.AR_ARCH_SYMMETRIC, sd=lambda: make_symmetric_state_dict(2, 7, 7), conc=4096, n=4096,
+                          arch=N.AR_ARCH_SYMMETRIC, sd=lambda: make_symmetric_state_dict(2, 7, 7), conc=4096, n=1024,
                           sims=2693, fpu=0.479, fk=0.025),
         "cnn": dict(config="4: 7x7_rust_strong + CNN res-res-gpool32 (64 ch), 4096 resident trees",
-                    arch=N.AR_ARCH_CNN, sd=lambda: make_cnn_state_dict(3, ("res", "res", "gpool")), conc=4096, n=2048,
+                    arch=N.AR_ARCH_CNN, sd=lambda: make_cnn_state_dict(3, ("res", "res", "gpool")), conc=4096, n=1024,
                     sims=2693, fpu=0.479, fk=0.025),
     }
 
