@@ -210,12 +210,14 @@ def nn_runs():
     return {
         "mlp": dict(config="3: 7x7_rust_tuned + MLP(hidden 256), 16384 resident trees", arch=N.AR_ARCH_MLP,
                     sd=lambda: make_mlp_state_dict(0, 349), conc=16384, n=16384, sims=1897, fpu=0.459, fk=0.103),
-        # config 4 runs are short (1024 games through at most 4096 trees): bounded bench time
-        "symmetric": dict(config="4: 7x7_rust_strong + SymmetricMLP(hidden 256), 4096 resident trees",
-                          arch=N.AR_ARCH_SYMMETRIC, sd=lambda: make_symmetric_state_dict(2, 7, 7), conc=4096, n=1024,
+        # config 4 runs are short (2048 games, one per resident tree) to bound the bench time; a run lasts as long as its
+        # longest game (the NN-guided loop is bulk-synchronous, one batch per tree and step), so S_new/s grows with the
+        # number of games per tree: 4096 games through 4096 trees gave 1.2e7 (SymmetricMLP) / 1.7e7 (CNN), cache off
+        "symmetric": dict(config="4: 7x7_rust_strong + SymmetricMLP(hidden 256), 2048 resident trees",
+                          arch=N.AR_ARCH_SYMMETRIC, sd=lambda: make_symmetric_state_dict(2, 7, 7), conc=2048, n=2048,
                           sims=2693, fpu=0.479, fk=0.025),
-        "cnn": dict(config="4: 7x7_rust_strong + CNN res-res-gpool32 (64 ch), 4096 resident trees",
-                    arch=N.AR_ARCH_CNN, sd=lambda: make_cnn_state_dict(3, ("res", "res", "gpool")), conc=4096, n=1024,
+        "cnn": dict(config="4: 7x7_rust_strong + CNN res-res-gpool32 (64 ch), 2048 resident trees",
+                    arch=N.AR_ARCH_CNN, sd=lambda: make_cnn_state_dict(3, ("res", "res", "gpool")), conc=2048, n=2048,
                     sims=2693, fpu=0.479, fk=0.025),
     }
 
@@ -539,10 +541,10 @@ def run_cuda(args) -> None:
         # every rank runs its own launches: per-GPU achieved bandwidth = per-GPU algorithmic bytes / device span
         achieved = algo_bytes / world / (dev_ms * 1e-3) / 1e9
         # `traffic`: DRAM bytes per launch.  The ncu --set full capture is taken on a bounded launch of the same
-        # kernel and workload (profiles/traffic_r1.json: measured DRAM bytes and that launch's algorithmic bytes);
+        # kernel and workload (profiles/traffic_r2.json: measured DRAM bytes and that launch's algorithmic bytes);
         # the ratio is applied to this run's algorithmic bytes per launch.
         traffic = None
-        tp = ROOT / "profiles" / "traffic_r1.json"
+        tp = ROOT / "profiles" / "traffic_r2.json"
         if tp.exists():
             tj = json.loads(tp.read_text())
             traffic = tj["dram_bytes"] / tj["algorithmic_bytes"] * algo_bytes / max(launches, 1)
