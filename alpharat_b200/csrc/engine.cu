@@ -347,20 +347,20 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(Ru
 // that the 32 trees of a warp reconverge at every step.
 // =========================================================================================
 constexpr int TT_BLOCK = 32;
-template <int MIN_BLOCKS>
+template <int MIN_BLOCKS, int NW>
 __global__ void __launch_bounds__(TT_BLOCK, MIN_BLOCKS) selfplay_tt_kernel(tt::Ctx c, int n_slots) {
-  extern __shared__ __align__(16) uint32_t tt_smem[];  // maze image: 16 words per tree, word-interleaved
+  using T = tt::TT<NW>;
+  extern __shared__ __align__(16) uint32_t tt_smem[];  // maze image: 16 * NW words per tree, word-interleaved
   const int slot = blockIdx.x * TT_BLOCK + threadIdx.x;
-  tt::TState s;
-  tt::TArr a;
-  tt::tt_init(s, c, (uint32_t)slot, tt_smem + threadIdx.x, TT_BLOCK);
+  typename T::TState s;
+  typename T::TArr a;
+  T::tt_init(s, c, (uint32_t)slot, tt_smem + threadIdx.x, TT_BLOCK);
   if (slot >= n_slots) s.phase = tt::PH_EXIT;
   const int lane = threadIdx.x & 31;
-  unsigned long long steps = 0;
   // Warp-level phase scheduler: every iteration runs ONE phase, the one most of the warp's trees are in;
-  // the others wait (they cost nothing) and pile up until their phase is the majority.  This keeps the
-  // lanes converged: a descend step is ~8x the instructions of a backup step, so running both every
-  // iteration (plain divergence) left 5.7 of 32 lanes active (profiles/r2_tt_v2_divergent.md).
+  // the others wait (they cost nothing) and pile up until their phase is the majority.  A descend step is
+  // ~8x the instructions of a backup step, so running both every iteration (plain divergence) left 5.7 of 32
+  // lanes active (profiles/r2_summary.md section 3).
   for (;;) {
     const unsigned md = __ballot_sync(0xffffffffu, s.phase == tt::PH_DESCEND);
     const unsigned mb = __ballot_sync(0xffffffffu, s.phase == tt::PH_BACKUP);
@@ -369,23 +369,22 @@ __global__ void __launch_bounds__(TT_BLOCK, MIN_BLOCKS) selfplay_tt_kernel(tt::C
     if (mc) {  // rare (a few per move) and it unblocks a tree: always first
       const unsigned need = __ballot_sync(0xffffffffu, s.phase == tt::PH_CONTROL && s.cstate == tt::CS_COMPACT_MARK);
       if (need) {
-        tt::coop_compact(s, c, need, lane);
+        T::coop_compact(s, c, need, lane);
       } else if (s.phase == tt::PH_CONTROL) {
-        tt::control<true>(s, c);
+        T::template control<true>(s, c);
       }
       continue;
     }
     if (__popc(mb) >= __popc(md)) {
-      if (s.phase == tt::PH_BACKUP) { tt::step_backup<true>(s, a, c); steps += 1; }
+      if (s.phase == tt::PH_BACKUP) T::template step_backup<true>(s, a, c);
     } else {
-      if (s.phase == tt::PH_DESCEND) { tt::step_descend<true>(s, a, c); steps += 1; }
+      if (s.phase == tt::PH_DESCEND) T::template step_descend<true>(s, a, c);
     }
   }
   atomicAdd(&c.counters[0], s.path_nodes);
   atomicAdd(&c.counters[1], s.new_nodes);
   if (s.error) atomicCAS(c.error_flag, 0, (int)s.error);
 }
-
 
 // Block-sorted variant: the trees' state lives in shared memory instead of registers, and every
 // iteration the block sorts its trees by phase, so a warp runs 32 trees that are all in the SAME phase
@@ -394,24 +393,29 @@ __global__ void __launch_bounds__(TT_BLOCK, MIN_BLOCKS) selfplay_tt_kernel(tt::C
 // (With trees bound to lanes 7.7 of 32 lanes were active on the real workload, profiles/r2_tt_lanes.md.)
 constexpr int TB_BLOCK = 128;
 constexpr int TB_BACKUP_NODES = 4;
-__host__ __device__ inline size_t tb_smem_bytes() { return (size_t)TB_BLOCK * (sizeof(tt::TState) + 64 + 2 + 2) + 256; }
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(TB_BLOCK, MIN_BLOCKS) selfplay_tb_kernel(tt::Ctx c, tt::TArr* arrs) {
+template <int NW>
+__host__ __device__ inline size_t tb_smem_bytes() {
+  return (size_t)TB_BLOCK * (sizeof(typename tt::TT<NW>::TState) + 4 * tt::TT<NW>::MAZE_WORDS + 2 + 2) + 256;
+}
+template <int MIN_BLOCKS, int NW>
+__global__ void __launch_bounds__(TB_BLOCK, MIN_BLOCKS) selfplay_tb_kernel(tt::Ctx c, typename tt::TT<NW>::TArr* arrs) {
+  using T = tt::TT<NW>;
+  using TState = typename T::TState;
+  using TArr = typename T::TArr;
   extern __shared__ __align__(16) uint8_t tb_smem[];
-  tt::TState* st = reinterpret_cast<tt::TState*>(tb_smem);
-  uint32_t* maze = reinterpret_cast<uint32_t*>(st + TB_BLOCK);              // [16][TB_BLOCK]
-  uint16_t* order = reinterpret_cast<uint16_t*>(maze + 16 * TB_BLOCK);      // trees sorted by phase
+  TState* st = reinterpret_cast<TState*>(tb_smem);
+  uint32_t* maze = reinterpret_cast<uint32_t*>(st + TB_BLOCK);              // [MAZE_WORDS][TB_BLOCK]
+  uint16_t* order = reinterpret_cast<uint16_t*>(maze + T::MAZE_WORDS * TB_BLOCK);  // trees sorted by phase
   uint16_t* creq = order + TB_BLOCK;                                        // trees that asked for a compaction
-  int* wcnt = reinterpret_cast<int*>(creq + TB_BLOCK);                      // [4 classes][4 warps] + totals
+  int* wcnt = reinterpret_cast<int*>(creq + TB_BLOCK);                      // [4 classes][4 warps]
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  constexpr int NW = TB_BLOCK / 32;
+  constexpr int NWARP = TB_BLOCK / 32;
   {
-    tt::TState s;
-    tt::tt_init(s, c, (uint32_t)(blockIdx.x * TB_BLOCK + tid), maze + tid, TB_BLOCK);
+    TState s;
+    T::tt_init(s, c, (uint32_t)(blockIdx.x * TB_BLOCK + tid), maze + tid, TB_BLOCK);
     st[tid] = s;
   }
-  tt::TArr* my_arrs = arrs + (size_t)blockIdx.x * TB_BLOCK;
-  unsigned long long steps = 0;
+  TArr* my_arrs = arrs + (size_t)blockIdx.x * TB_BLOCK;
   __syncthreads();
   for (;;) {
     // ---- classify this thread's own tree: 0 descend, 1 backup, 2 control, 3 compaction request, 4 exited
@@ -421,7 +425,7 @@ __global__ void __launch_bounds__(TB_BLOCK, MIN_BLOCKS) selfplay_tb_kernel(tt::C
     unsigned bal[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) bal[k] = __ballot_sync(0xffffffffu, cls == k);
-    if (lane < 4) wcnt[lane * NW + wid] = __popc(bal[lane]);
+    if (lane < 4) wcnt[lane * NWARP + wid] = __popc(bal[lane]);
     __syncthreads();
     // ---- ranks: class-major, then warp, then lane
     int base[4], total = 0, n_creq = 0;
@@ -429,8 +433,8 @@ __global__ void __launch_bounds__(TB_BLOCK, MIN_BLOCKS) selfplay_tb_kernel(tt::C
     for (int k = 0; k < 4; ++k) {
       int before = 0, all = 0;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        const int v = wcnt[k * NW + w];
+      for (int w = 0; w < NWARP; ++w) {
+        const int v = wcnt[k * NWARP + w];
         before += w < wid ? v : 0;
         all += v;
       }
@@ -441,13 +445,13 @@ __global__ void __launch_bounds__(TB_BLOCK, MIN_BLOCKS) selfplay_tb_kernel(tt::C
     else if (cls == 3) creq[base[3] + __popc(bal[3] & ((1u << lane) - 1u))] = (uint16_t)tid;
     __syncthreads();
     // ---- compaction requests: one warp per tree, all 32 lanes (tree_thread.cuh coop_compact_tree)
-    for (int r = wid; r < n_creq; r += NW) {
-      tt::TState& ts = st[creq[r]];
-      const uint32_t kept = tt::coop_compact_tree(ts.pt, c.arena, ts.cp_count, ts.cp_new_root, ts.cp_page0, ts.cp_page1,
+    for (int r = wid; r < n_creq; r += NWARP) {
+      TState& ts = st[creq[r]];
+      const uint32_t kept = T::coop_compact_tree(ts.pt, c.arena, ts.cp_count, ts.cp_new_root, ts.cp_page0, ts.cp_page1,
                                                   ts.cp_page2, ts.cp_page3, lane);
       if (lane == 0) {
         ts.cp_kept = kept;
-        tt::compact_end(ts, c);
+        T::compact_end(ts, c);
         ts.cstate = tt::CS_MOVE_START;
       }
       __syncwarp();
@@ -455,13 +459,12 @@ __global__ void __launch_bounds__(TB_BLOCK, MIN_BLOCKS) selfplay_tb_kernel(tt::C
     // ---- one step for the tree of this thread's rank
     if (tid < total) {
       const int tree = order[tid];
-      tt::TState s = st[tree];
-      tt::TArr& a = my_arrs[tree];
-      if (s.phase == tt::PH_DESCEND) tt::step_descend<true>(s, a, c);
-      else if (s.phase == tt::PH_BACKUP) tt::step_backup<true>(s, a, c, TB_BACKUP_NODES);
-      else tt::control<true>(s, c);
+      TState s = st[tree];
+      TArr& a = my_arrs[tree];
+      if (s.phase == tt::PH_DESCEND) T::template step_descend<true>(s, a, c);
+      else if (s.phase == tt::PH_BACKUP) T::template step_backup<true>(s, a, c, TB_BACKUP_NODES);
+      else T::template control<true>(s, c);
       st[tree] = s;
-      steps += 1;
     }
     __syncthreads();
   }
@@ -949,7 +952,7 @@ struct ar_engine {
   uint32_t* tt_bitmap = nullptr;
   uint32_t* tt_page_tables = nullptr;
   uint32_t tt_n_pages = 0, tt_bitmap_words = 0, tt_pt_stride = 0, tt_slots = 0;
-  tt::TArr* tt_arrs = nullptr;  // per-tree cell stack + batch entries of the block-sorted kernel
+  void* tt_arrs = nullptr;      // per-tree cell stack + batch entries of the block-sorted kernel (TT<NW>::TArr)
   // per-slot storage of the warp-per-tree NN-guided engine (allocated on first use)
   NodeRec* pools = nullptr;
   uint32_t* path_bufs = nullptr;
@@ -1041,9 +1044,10 @@ static ar_status validate_games(ar_engine* e, const ar_game_pod* games, int n) {
     const ar_game_pod& g = games[i];
     uint32_t cells = (uint32_t)g.width * g.height;
     if (g.width == 0 || g.height == 0) { e->err = "game " + std::to_string(i) + ": empty board"; return AR_ERR_INVALID_ARG; }
-    if (cells > 64 || cells > e->cfg.max_cells) {
+    if (cells > e->cfg.max_cells || g.width > 16 || g.height > 16) {
       e->err = "game " + std::to_string(i) + ": " + std::to_string(g.width) + "x" + std::to_string(g.height) +
-               " board exceeds the 64-cell bitboard of this build";
+               " board exceeds the engine's max_cells (" + std::to_string(e->cfg.max_cells) +
+               "; boards over 64 cells need tree_engine = AR_TREE_THREAD and no evaluator)";
       return AR_ERR_UNSUPPORTED;
     }
     if (g.max_turns > e->cfg.max_turns) {
@@ -1165,7 +1169,9 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
   };
   if (cfg->concurrent_games == 0) return fail(AR_ERR_INVALID_ARG, "concurrent_games must be > 0");
   if (cfg->tree_engine > AR_TREE_THREAD) return fail(AR_ERR_INVALID_ARG, "tree_engine must be AR_TREE_WARP or AR_TREE_THREAD");
-  if (cfg->max_cells == 0 || cfg->max_cells > 64) return fail(AR_ERR_UNSUPPORTED, "max_cells must be in [1, 64] in this build");
+  if (cfg->max_cells == 0 || cfg->max_cells > AR_MAX_CELLS) return fail(AR_ERR_UNSUPPORTED, "max_cells must be in [1, 256]");
+  if (cfg->max_cells > 64 && cfg->tree_engine != AR_TREE_THREAD)
+    return fail(AR_ERR_UNSUPPORTED, "boards over 64 cells need tree_engine = AR_TREE_THREAD (the warp engine and the evaluators keep a one-word cheese bitboard)");
   if (cfg->max_batch_size == 0 || cfg->max_batch_size > MAX_BATCH) return fail(AR_ERR_INVALID_ARG, "max_batch_size must be in [1, 64]");
   if (cfg->max_turns == 0 || cfg->max_turns > 250) return fail(AR_ERR_UNSUPPORTED, "max_turns must be in [1, 250] in this build (8-bit path depth)");
   cudaError_t ce = cudaSetDevice(cfg->device);
@@ -1247,7 +1253,11 @@ ar_status ar_engine_load_weights(ar_engine* e, int32_t arch, int32_t width, int3
     e->err = "unknown architecture " + std::to_string(arch);
     return AR_ERR_UNSUPPORTED;
   }
-  if (width <= 0 || height <= 0 || width * height > 64) { e->err = "bad board size"; return AR_ERR_INVALID_ARG; }
+  if (width <= 0 || height <= 0) { e->err = "bad board size"; return AR_ERR_INVALID_ARG; }
+  if (width * height > 64 || e->cfg.max_cells > 64) {
+    e->err = "the leaf evaluators support boards of up to 64 cells (engine max_cells must be <= 64 too)";
+    return AR_ERR_UNSUPPORTED;
+  }
   if (!tensors || n_tensors <= 0) { e->err = "no tensors"; return AR_ERR_INVALID_ARG; }
   LeafEvaluator* ev = arch == AR_ARCH_MLP ? static_cast<LeafEvaluator*>(new MlpModel())
                       : arch == AR_ARCH_SYMMETRIC ? make_symmetric_evaluator() : make_cnn_evaluator();
@@ -1312,9 +1322,10 @@ static ar_status ensure_tt(ar_engine* e) {
   CK(cudaMalloc(&e->tt_arena, (size_t)pages * tt::PAGE_BYTES));
   CK(cudaMalloc(&e->tt_bitmap, (size_t)e->tt_bitmap_words * sizeof(uint32_t)));
   CK(cudaMalloc(&e->tt_page_tables, (size_t)e->tt_slots * e->tt_pt_stride * sizeof(uint32_t)));
-  CK(cudaMalloc(&e->tt_arrs, (size_t)e->tt_slots * sizeof(tt::TArr)));
-  CK(cudaFuncSetAttribute(selfplay_tb_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem_bytes()));
-  CK(cudaFuncSetAttribute(selfplay_tb_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem_bytes()));
+  const bool big = e->cfg.max_cells > 64;  // boards over 64 cells: the four-word cheese bitboard instantiation
+  CK(cudaMalloc(&e->tt_arrs, (size_t)e->tt_slots * (big ? sizeof(tt::TT<4>::TArr) : sizeof(tt::TT<1>::TArr))));
+  CK(cudaFuncSetAttribute(selfplay_tb_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem_bytes<1>()));
+  CK(cudaFuncSetAttribute(selfplay_tb_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem_bytes<4>()));
   return AR_OK;
 }
 
@@ -1440,18 +1451,23 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
     c.error_flag = e->cur->d_error;
     c.progress = p.progress;
     const int tslots = (std::min<int>((int)e->tt_slots, std::max(p.n_games, 1)) + TB_BLOCK - 1) / TB_BLOCK * TB_BLOCK;
-    static const int variant = [] { const char* v = getenv("AR_TT_KERNEL"); return v ? atoi(v) : 1; }();  // 0 lane-bound, 1 block-sorted
-    if (variant == 1) {
-      static const int tb_minb = [] { const char* v = getenv("AR_TB_BLOCKS_PER_SM"); return v ? atoi(v) : 3; }();
-      if (tb_minb >= 4) selfplay_tb_kernel<4><<<tslots / TB_BLOCK, TB_BLOCK, tb_smem_bytes(), e->cur->stream>>>(c, e->tt_arrs);
-      else selfplay_tb_kernel<3><<<tslots / TB_BLOCK, TB_BLOCK, tb_smem_bytes(), e->cur->stream>>>(c, e->tt_arrs);
-    } else {
-    // resident warps per SM (register budget): experiment knob, default 12
+    // AR_TT_KERNEL: 0 = lane-bound (a tree stays on its lane; the faster of the two, default), 1 = block-sorted (tree
+    // state in shared memory, trees sorted by phase every iteration); AR_TT_WARPS_PER_SM: register budget of variant 0
+    static const int variant = [] { const char* v = getenv("AR_TT_KERNEL"); return v ? atoi(v) : 0; }();
     static const int minb = [] { const char* v = getenv("AR_TT_WARPS_PER_SM"); return v ? atoi(v) : 12; }();
-    if (minb >= 20) selfplay_tt_kernel<20><<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->cur->stream>>>(c, tslots);
-    else if (minb >= 16) selfplay_tt_kernel<16><<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->cur->stream>>>(c, tslots);
-    else if (minb >= 12) selfplay_tt_kernel<12><<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->cur->stream>>>(c, tslots);
-    else selfplay_tt_kernel<8><<<tslots / TT_BLOCK, TT_BLOCK, TT_BLOCK * 64, e->cur->stream>>>(c, tslots);
+    const bool big = e->cfg.max_cells > 64;
+    const int nb = tslots / TT_BLOCK;
+    if (big) {
+      if (variant == 1) selfplay_tb_kernel<2, 4><<<tslots / TB_BLOCK, TB_BLOCK, tb_smem_bytes<4>(), e->cur->stream>>>(c, (tt::TT<4>::TArr*)e->tt_arrs);
+      else selfplay_tt_kernel<8, 4><<<nb, TT_BLOCK, TT_BLOCK * 4 * tt::TT<4>::MAZE_WORDS, e->cur->stream>>>(c, tslots);
+    } else if (variant == 1) {
+      selfplay_tb_kernel<3, 1><<<tslots / TB_BLOCK, TB_BLOCK, tb_smem_bytes<1>(), e->cur->stream>>>(c, (tt::TT<1>::TArr*)e->tt_arrs);
+    } else {
+      const size_t sm = TT_BLOCK * 4 * tt::TT<1>::MAZE_WORDS;
+      if (minb >= 20) selfplay_tt_kernel<20, 1><<<nb, TT_BLOCK, sm, e->cur->stream>>>(c, tslots);
+      else if (minb >= 16) selfplay_tt_kernel<16, 1><<<nb, TT_BLOCK, sm, e->cur->stream>>>(c, tslots);
+      else if (minb >= 12) selfplay_tt_kernel<12, 1><<<nb, TT_BLOCK, sm, e->cur->stream>>>(c, tslots);
+      else selfplay_tt_kernel<8, 1><<<nb, TT_BLOCK, sm, e->cur->stream>>>(c, tslots);
     }
     CK(cudaGetLastError());
     e->cur->launches += 1;

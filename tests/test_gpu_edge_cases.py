@@ -109,9 +109,45 @@ def test_loud_failures():
         with pytest.raises(ValueError, match="max_turns"):
             eng.selfplay(pods_array(make_games(1, width=5, height=5, cheese_count=5, max_turns=80)),
                          search_cfg(simulations=10, batch_size=8), [0])
-        with pytest.raises((NotImplementedError, RuntimeError), match="64-cell"):  # 81 cells > the 64-cell bitboard
+        with pytest.raises((NotImplementedError, RuntimeError), match="max_cells"):  # 81 cells > this engine's 64
             eng.selfplay(pods_array([GameSpec(9, 9, 10, (0, 0), (8, 8), [(4, 4)])]),
                          search_cfg(simulations=10, batch_size=8), [0])
+    with pytest.raises(NotImplementedError, match="AR_TREE_THREAD"):  # big boards: thread engine only
+        Engine(concurrent_games=4, max_turns=50, max_cells=256)
+    with Engine(concurrent_games=4, max_turns=50, max_cells=256, tree_engine="thread") as eng:
+        from nn_ref import make_mlp_state_dict
+        from alpharat_b200 import _native as N
+
+        with pytest.raises(NotImplementedError, match="64 cells"):  # evaluators keep the one-word bitboard
+            eng.load_weights(N.AR_ARCH_MLP, 7, 7, make_mlp_state_dict(0, 349))
+
+
+def test_boards_over_64_cells_on_the_thread_engine(oracle):
+    """11x11 / 15x15 (the reference's search benches, crates/alpharat-mcts/benches/search.rs:36-78) and 16x16, the largest
+    board an ar_game_pod holds: self-play and fresh-tree search on `tree_engine="thread"` (four-word cheese bitboard),
+    bit-exact against the oracle."""
+    cfg = search_cfg(simulations=200, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103)
+    with Engine(concurrent_games=32, max_turns=40, max_batch_size=16, max_simulations=200, max_cells=256,
+                tree_engine="thread") as eng:
+        for specs, seeds in (
+            (make_games(24, width=11, height=11, cheese_count=21, max_turns=40, first_index=11), [70 + i for i in range(24)]),
+            (make_games(12, width=16, height=16, cheese_count=40, max_turns=30, maze_type="classic", positions="random",
+                        first_index=16), [5 + i for i in range(12)]),
+        ):
+            pods = pods_array(specs)
+            gpu = eng.selfplay(pods, cfg, seeds)
+            cpu = oracle_selfplay(oracle, pods, cfg, seeds)
+            compare_selfplay(gpu, cpu, len(specs))
+    specs = make_games(16, width=15, height=15, cheese_count=41, max_turns=200, first_index=15)
+    pods = pods_array(specs)
+    cfg = search_cfg(simulations=5000, batch_size=64)
+    with Engine(concurrent_games=16, max_turns=200, max_batch_size=64, max_simulations=5000, max_cells=256,
+                tree_engine="thread") as eng:
+        out = eng.search_batch(pods, cfg, list(range(16)))
+    for i in range(16):
+        rc, ref, clean = oracle_search(oracle, pods[i], cfg, i)
+        assert rc == 0 and clean
+        assert_result_equal(out[i], ref, f"15x15 pos {i}")
 
 
 def test_run_cuda_sampling_writes_a_registered_batch(oracle, tmp_path):

@@ -82,3 +82,24 @@ def test_search_batch_edge_positions(emul, oracle):
             rc, ref, clean = oracle_search(oracle, pods[i], cfg, seeds[i])
             assert rc == 0 and clean
             assert_result_equal(out[i], ref, f"sims={sims} bs={bs} pos {i}")
+
+
+def test_boards_over_64_cells(emul, oracle):
+    """11x11 and 15x15 (the sizes of the reference's search benches, crates/alpharat-mcts/benches/search.rs:36-78) and the
+    largest board an ar_game_pod holds (16x16): the thread engine's four-word cheese bitboard, self-play and search."""
+    n = 10
+    _check(emul, oracle, make_games(n, width=11, height=11, cheese_count=21, max_turns=40, first_index=11),
+           search_cfg(simulations=200, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103),
+           [70 + i for i in range(n)], n_threads=8)
+    n = 6
+    _check(emul, oracle, make_games(n, width=16, height=16, cheese_count=40, max_turns=30, maze_type="classic",
+                                    positions="random", first_index=16),
+           search_cfg(simulations=150, batch_size=8), [5 + i for i in range(n)], n_threads=4)
+    specs = make_games(6, width=15, height=15, cheese_count=41, max_turns=200, first_index=15)
+    pods = pods_array(specs)
+    cfg = search_cfg(simulations=2000, batch_size=64)
+    out = emul_search(emul, pods, cfg, list(range(6)), n_threads=3)
+    for i in range(6):
+        rc, ref, clean = oracle_search(oracle, pods[i], cfg, i)
+        assert rc == 0 and clean
+        assert_result_equal(out[i], ref, f"15x15 pos {i}")

@@ -13,11 +13,31 @@
 #include "../../alpharat_b200/csrc/host_tables.hpp"
 #include "../../alpharat_b200/csrc/tree_thread.cuh"
 
+template <int NW>
+static int run_nw(const ar_game_pod* games, int n, const ar_search_cfg* cfg, const uint64_t* seeds,
+                  int n_threads, int n_pages, int search_only, ar_game_summary* summaries,
+                  ar_position_record* positions, int stride, ar_search_result* search_out,
+                  unsigned long long* counters);
+
 extern "C" int tt_emul_run(const ar_game_pod* games, int n, const ar_search_cfg* cfg, const uint64_t* seeds,
                            int n_threads, int n_pages, int search_only, ar_game_summary* summaries,
                            ar_position_record* positions, int stride, ar_search_result* search_out,
                            unsigned long long* counters /* [4]: path_nodes new_nodes peak_pages steps */) {
+  bool big = false;  // boards over 64 cells need the 4-word cheese bitboard
+  for (int i = 0; i < n; ++i) big = big || (int)games[i].width * games[i].height > 64;
+  return big ? run_nw<4>(games, n, cfg, seeds, n_threads, n_pages, search_only, summaries, positions, stride, search_out, counters)
+             : run_nw<1>(games, n, cfg, seeds, n_threads, n_pages, search_only, summaries, positions, stride, search_out, counters);
+}
+
+template <int NW>
+static int run_nw(const ar_game_pod* games, int n, const ar_search_cfg* cfg, const uint64_t* seeds,
+                  int n_threads, int n_pages, int search_only, ar_game_summary* summaries,
+                  ar_position_record* positions, int stride, ar_search_result* search_out,
+                  unsigned long long* counters) {
   using namespace tt;
+  using T = TT<NW>;
+  using TState = typename T::TState;
+  using TArr = typename T::TArr;
   if (n_threads < 1 || n_pages < n_threads) return -1;
   Ctx c;
   memset(&c, 0, sizeof(c));
@@ -51,17 +71,17 @@ extern "C" int tt_emul_run(const ar_game_pod* games, int n, const ar_search_cfg*
   c.error_flag = &err;
   c.progress = nullptr;
 
-  std::vector<uint32_t> maze((size_t)16 * n_threads, 0);
+  std::vector<uint32_t> maze((size_t)T::MAZE_WORDS * n_threads, 0);
   std::vector<TState> st(n_threads);
   std::vector<TArr> arr(n_threads);
-  for (int t = 0; t < n_threads; ++t) tt_init(st[t], c, (uint32_t)t, maze.data() + t, n_threads);
+  for (int t = 0; t < n_threads; ++t) T::tt_init(st[t], c, (uint32_t)t, maze.data() + t, n_threads);
   unsigned long long steps = 0, peak = 0;
   for (;;) {
     int alive = 0;
     for (int t = 0; t < n_threads; ++t) {
       if (st[t].phase == PH_EXIT) continue;
       alive += 1;
-      tt_step<false>(st[t], arr[t], c);
+      T::template tt_step<false>(st[t], arr[t], c);
       steps += 1;
     }
     if ((steps & 0xfff) < (unsigned)n_threads) {
