@@ -1396,6 +1396,11 @@ static ar_status ensure_nn_buffers(ar_engine* e) {
 }
 
 static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_progress, float* ms) {
+  for (const BatchBuf* b : e->sbufs)
+    if (b->in_flight) {  // a blocking launch takes its tree slots by block index, streaming launches by bitmap
+      e->err = "a streaming batch is in flight: collect it (ar_stream_collect / ar_stream_wait) before a blocking call";
+      return AR_ERR_INVALID_ARG;
+    }
   CK(cudaMemsetAsync(e->cur->d_next, 0, sizeof(unsigned int), e->cur->stream));
   CK(cudaMemsetAsync(e->cur->d_counters, 0, 8 * sizeof(unsigned long long), e->cur->stream));
   CK(cudaMemsetAsync(e->cur->d_error, 0, sizeof(int), e->cur->stream));

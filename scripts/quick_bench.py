@@ -1,6 +1,7 @@
 """Steady-state probe of the uniform self-play kernel: N games (32768 distinct layouts tiled, distinct seeds)
 through CONC resident trees; prints device-timed S_new/s.  usage: quick_bench.py N CONC [REPEATS]"""
 import ctypes as C
+import os
 import sys, time
 sys.path.insert(0,'.')
 from alpharat_b200 import _native as N
@@ -15,7 +16,8 @@ for off in range(0, n, base):
     m = min(base, n - off)
     C.memmove(C.byref(pods, off * sz), pods0, m * sz)
 cfg = search_cfg(simulations=1897, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103)
-eng = Engine(concurrent_games=conc, max_turns=50, max_batch_size=16, max_simulations=1897)
+eng = Engine(concurrent_games=conc, max_turns=50, max_batch_size=16, max_simulations=1897,
+             tree_engine=os.environ.get("AR_TREE_ENGINE", "warp"))  # AR_TREE_ENGINE=thread: the thread-per-tree engine
 eng.selfplay_upload(pods, list(range(n)))
 for it in range(int(sys.argv[3]) if len(sys.argv)>3 else 1):
     st = eng.selfplay_run_resident(cfg)
