@@ -35,6 +35,7 @@ from __future__ import annotations
 import argparse
 import ctypes as C
 import json
+import multiprocessing as mp
 import os
 import queue
 import statistics
@@ -42,6 +43,7 @@ import subprocess
 import sys
 import threading
 import time
+from concurrent.futures import ProcessPoolExecutor
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
@@ -138,6 +140,21 @@ def make_batch(n: int, first_index: int):
     specs = make_games(n, first_index=first_index, **WORKLOAD)
     seeds = (C.c_uint64 * max(n, 1))(*[first_index + i for i in range(n)])
     return pods_array(specs), seeds
+
+
+def make_batch_bytes(n: int, first_index: int) -> bytes:
+    """Worker-process half of the batch feeder: the pods of one batch as bytes (building 131072 games takes about as
+    long in Python as the GPU needs to play them, so the feeder builds several batches in parallel)."""
+    pods, _ = make_batch(n, first_index)
+    return bytes(memoryview(pods).cast("B"))
+
+
+def batch_from_bytes(raw: bytes, n: int, first_index: int):
+    from alpharat_b200 import _native as N
+
+    pods = (N.GamePod * max(n, 1)).from_buffer_copy(raw)
+    seeds = (C.c_uint64 * max(n, 1))(*range(first_index, first_index + n))
+    return pods, seeds
 
 
 def cpu_baseline(seconds: float, threads: int, first_index: int = 10_000_000) -> dict:
@@ -395,15 +412,22 @@ def run_cuda(args) -> None:
     def first_index(step: int) -> int:  # fresh games every step, disjoint across ranks
         return (step * world + rank) * n
 
-    # Batches are built by a feeder thread, ahead of the step that plays them (building one in Python takes about
-    # as long as playing it; the engine calls release the GIL), so host memory does not grow with --steps.
+    # Batches are built ahead of the step that plays them by worker processes (building one in Python takes about
+    # as long as playing it), a few at a time, so the GPU never waits for the host and host memory does not grow
+    # with --steps.
     total_steps = args.warmup + args.steps
     feed: queue.Queue = queue.Queue(maxsize=2)
 
     def feeder() -> None:
         try:
-            for i in range(total_steps):
-                feed.put(make_batch(n, first_index(i)))
+            with ProcessPoolExecutor(max_workers=args.feed_workers, mp_context=mp.get_context("spawn")) as pool:
+                ahead = []
+                nxt = 0
+                for i in range(total_steps):
+                    while nxt < total_steps and len(ahead) < args.feed_workers + 1:
+                        ahead.append(pool.submit(make_batch_bytes, n, first_index(nxt)))
+                        nxt += 1
+                    feed.put(batch_from_bytes(ahead.pop(0).result(), n, first_index(i)))
         except BaseException as exc:  # surfaces in the consumer instead of hanging it
             feed.put(exc)
 
@@ -598,6 +622,7 @@ def main() -> None:
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--games-per-step", type=int, default=131072)
     ap.add_argument("--concurrent", type=int, default=4096)
+    ap.add_argument("--feed-workers", type=int, default=3, help="processes that build the synthetic batches")
     ap.add_argument("--e2e-keep", type=int, default=4, help="distinct batches kept in host memory for the e2e leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-seconds", type=float, default=10.0)
