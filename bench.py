@@ -7,7 +7,7 @@ Workload (BASELINE.json configs[1]): PyRat 7x7 open maze, 10 cheese, 50 turns, `
 (1897 sims, c_puct 0.512, fpu 0.459, force_k 0.103, batch 16), uniform priors, Dirichlet noise 0,
 4096 resident game trees per GPU (one warp each).  One step = one pass of the hot path over one batch of
 synthetic games (`--games-per-step` per GPU, default 131072, fresh games every step, played to completion).
-Steps are fed continuously (ar_stream_*: up to three batches in flight, the next batch's blocks take over the
+Steps are fed continuously (ar_stream_*: three to eight batches in flight, the next batch's blocks take over the
 SMs as the previous batch's last long games finish), so throughput does not depend on the batch size.
 
 Metric: self-play MCTS simulations/sec, counted as S_new = descents performed
@@ -54,7 +54,6 @@ SEARCH = dict(simulations=1897, batch_size=16, c_puct=0.512, fpu_reduction=0.459
               noise_epsilon=0.0)
 BYTES_PER_NODE_VISIT = 288
 BYTES_PER_NEW_NODE = 240
-N_BUFFERS = 3
 
 
 def measured_peaks() -> dict:
@@ -130,8 +129,14 @@ def bench_config(args, world: int) -> dict:
         "parallelism": f"games sharded over {world} GPU(s), no data-path collective",
         "l2": "per-GPU node pools (GBs) exceed the 126 MB L2; fresh games every step",
         "simulations_definition": "S_new = nn_evals + terminals (descents performed)",
-        "feed": f"continuous: {N_BUFFERS} batches in flight (ar_stream_*), one tail per run instead of one per step",
+        "feed": f"continuous: {n_buffers(args)} batches in flight (ar_stream_*), one tail per run instead of one per step",
     }
+
+
+def n_buffers(args) -> int:
+    """Batches in flight.  A batch lives much longer than its share of the throughput (its last games run alone while
+    the next batches fill the machine), so small batches need more of them in flight to keep the GPU fed."""
+    return max(3, min(8, (262144 + args.games_per_step - 1) // max(args.games_per_step, 1)))
 
 
 def make_batch(n: int, first_index: int):
@@ -407,6 +412,7 @@ def run_cuda(args) -> None:
     stride = WORKLOAD["max_turns"]
     eng = Engine(device=local, concurrent_games=args.concurrent, max_turns=stride,
                  max_batch_size=SEARCH["batch_size"], max_simulations=SEARCH["simulations"])
+    N_BUFFERS = n_buffers(args)
     eng.stream_open(N_BUFFERS, n, stride)
 
     def first_index(step: int) -> int:  # fresh games every step, disjoint across ranks
