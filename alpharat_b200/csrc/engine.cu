@@ -157,13 +157,16 @@ __device__ __forceinline__ void load_game(const ar_game_pod* pod, WarpCtx& cx, G
 #ifndef AR_MIN_BLOCKS
 #define AR_MIN_BLOCKS 7
 #endif
-__global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(RunParams p) {
+// WPB = warps per block: 4 for a blocking launch; 1 for streaming launches, where a finished warp must give its
+// SM resources back at once (in a 4-warp block the three early finishers idle until the last warp's games end).
+template <int WPB>
+__global__ void __launch_bounds__(32 * WPB, AR_MIN_BLOCKS * 4 / WPB) selfplay_uniform_kernel(RunParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   int lane = threadIdx.x & 31;
   asm volatile("" : "+r"(lane));
   const int wib = threadIdx.x >> 5;
   // Streaming launches overlap in time (batch b+1 fills the SMs as batch b's last games drain), so a
-  // block cannot own the slots of its blockIdx: it claims a free group of 4 tree slots instead.
+  // block cannot own the slots of its blockIdx: it claims a free group of WPB tree slots instead.
   __shared__ int s_group;
   int group = blockIdx.x;
   if (p.slot_bitmap) {
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(Ru
     __syncthreads();
     group = s_group;
   }
-  const int slot = group * 4 + wib;
+  const int slot = group * WPB + wib;
   if (slot >= p.n_slots) return;
 
   uint8_t* base = smem + (size_t)wib * warp_smem_bytes(p.max_depth, p.batch_cap);
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(128, AR_MIN_BLOCKS) selfplay_uniform_kernel(Ru
 #endif
     if (cx.error) atomicCAS(p.error_flag, 0, (int)cx.error);
   }
-  if (p.slot_bitmap) {  // n_slots is a multiple of 4 in streaming mode: every warp of the block gets here
+  if (p.slot_bitmap) {  // n_slots is a multiple of WPB in streaming mode: every warp of the block gets here
     __syncthreads();
     if (threadIdx.x == 0) atomicAnd(&p.slot_bitmap[group >> 5], ~(1u << (group & 31)));
   }
@@ -942,7 +945,7 @@ struct ar_engine {
   BatchBuf main;
   BatchBuf* cur = &main;                       // the batch the internal helpers operate on
   std::vector<BatchBuf*> sbufs;                // ar_stream_open
-  uint32_t* d_slot_bitmap = nullptr;           // slot groups (4 trees) in use by streaming launches
+  uint32_t* d_slot_bitmap = nullptr;           // tree slots in use by streaming launches
   cudaEvent_t ev_base = nullptr;               // time origin of ar_stream_times
   cudaStream_t stream2 = nullptr;              // second slot group of the NN-guided loop
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -1209,7 +1212,8 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
   CKC(cudaMalloc(&e->coll_table, (size_t)e->coll_len * sizeof(uint16_t)));
   CKC(cudaHostAlloc(&e->h_progress, sizeof(ar_progress), cudaHostAllocMapped));
   CKC(cudaHostGetDevicePointer(&e->d_progress, e->h_progress, 0));
-  CKC(cudaFuncSetAttribute(selfplay_uniform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CKC(cudaFuncSetAttribute(selfplay_uniform_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CKC(cudaFuncSetAttribute(selfplay_uniform_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem / 4));
   CKC(cudaFuncSetAttribute(nn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #undef CKC
   *out = e;
@@ -1431,7 +1435,7 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
   }
   CK(cudaEventRecord(e->cur->ev0, e->cur->stream));
   if (!nn && !tt_run) {
-    selfplay_uniform_kernel<<<(slots + 3) / 4, 128, smem, e->cur->stream>>>(p);
+    selfplay_uniform_kernel<4><<<(slots + 3) / 4, 128, smem, e->cur->stream>>>(p);
     CK(cudaGetLastError());
     e->cur->launches += 1;
   } else if (tt_run) {
@@ -1952,8 +1956,8 @@ ar_status ar_stream_open(ar_engine* e, int32_t n_buffers, int32_t max_games, int
   CK(cudaEventRecord(e->ev_base, e->main.stream));
   CK(cudaStreamSynchronize(e->main.stream));
   if (!e->d_slot_bitmap) {
-    CK(cudaMalloc(&e->d_slot_bitmap, (size_t)((e->n_slots / 4 + 31) / 32 + 1) * sizeof(uint32_t)));
-    CK(cudaMemset(e->d_slot_bitmap, 0, (size_t)((e->n_slots / 4 + 31) / 32 + 1) * sizeof(uint32_t)));
+    CK(cudaMalloc(&e->d_slot_bitmap, (size_t)((e->n_slots + 31) / 32 + 1) * sizeof(uint32_t)));
+    CK(cudaMemset(e->d_slot_bitmap, 0, (size_t)((e->n_slots + 31) / 32 + 1) * sizeof(uint32_t)));
   }
   return AR_OK;
 }
@@ -1983,7 +1987,6 @@ ar_status ar_stream_launch(ar_engine* e, int32_t buffer, const ar_search_cfg* cf
   if (s) return s;
   s = ensure_nn_pools(e);
   if (s) return s;
-  if (e->n_slots < 4) { e->err = "streaming needs at least 4 resident trees"; return AR_ERR_INVALID_ARG; }
   e->cur = b;
   RunParams p = make_params(e, cfg);
   e->cur = &e->main;
@@ -1992,8 +1995,8 @@ ar_status ar_stream_launch(ar_engine* e, int32_t buffer, const ar_search_cfg* cf
   p.summaries = b->d_summaries; p.positions = b->d_positions; p.pos_stride = b->resident_stride;
   p.search_only = 0;
   p.slot_bitmap = e->d_slot_bitmap;
-  p.n_groups = (int)e->n_slots / 4;
-  p.n_slots = p.n_groups * 4;
+  p.n_groups = (int)e->n_slots;  // one warp per block: a group is one tree slot
+  p.n_slots = p.n_groups;
   p.progress = nullptr;
   b->launches = 0;
   b->t_submit = std::chrono::steady_clock::now();
@@ -2002,9 +2005,9 @@ ar_status ar_stream_launch(ar_engine* e, int32_t buffer, const ar_search_cfg* cf
   CK(cudaMemsetAsync(b->d_error, 0, sizeof(int), b->stream));
   CK(cudaEventRecord(b->ev0, b->stream));
   if (b->n_resident > 0) {
-    const size_t smem = 4 * warp_smem_bytes(e->max_depth, e->batch_cap);
-    const int blocks = std::min(p.n_groups, (b->n_resident + 3) / 4);
-    selfplay_uniform_kernel<<<blocks, 128, smem, b->stream>>>(p);
+    const size_t smem = warp_smem_bytes(e->max_depth, e->batch_cap);
+    const int blocks = std::min(p.n_groups, b->n_resident);
+    selfplay_uniform_kernel<1><<<blocks, 32, smem, b->stream>>>(p);
     CK(cudaGetLastError());
     b->launches = 1;
   }
