@@ -555,12 +555,16 @@ __global__ void nn_init_slots_kernel(SlotState* slots, int n) {
   slots[i] = st;
 }
 
-__global__ void __launch_bounds__(128, AR_MIN_BLOCKS) nn_step_kernel(RunParams p, NnParams q) {
+// WPB = warps per block (AR_NN_WPB, default 1): the step is bulk-synchronous and its slots finish at very different
+// times (a 16-leaf batch, a one-leaf batch, a slice of a tree compaction); with one warp per block a finished slot
+// frees its share of the SM at once for the other slot group's step kernel.
+template <int WPB>
+__global__ void __launch_bounds__(32 * WPB, AR_MIN_BLOCKS * 4 / WPB) nn_step_kernel(RunParams p, NnParams q) {
   extern __shared__ __align__(16) uint8_t smem[];
   int lane = threadIdx.x & 31;
   asm volatile("" : "+r"(lane));
   const int wib = threadIdx.x >> 5;
-  const int slot = q.slot_begin + blockIdx.x * 4 + wib;
+  const int slot = q.slot_begin + blockIdx.x * WPB + wib;
   if (slot >= q.slot_end) return;
   SlotState* sp_g = q.slots + slot;
   if (sp_g->phase == PH_DONE) return;
@@ -1214,7 +1218,8 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
   CKC(cudaHostGetDevicePointer(&e->d_progress, e->h_progress, 0));
   CKC(cudaFuncSetAttribute(selfplay_uniform_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CKC(cudaFuncSetAttribute(selfplay_uniform_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem / 4));
-  CKC(cudaFuncSetAttribute(nn_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CKC(cudaFuncSetAttribute(nn_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CKC(cudaFuncSetAttribute(nn_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem / 4));
 #undef CKC
   *out = e;
   return AR_OK;
@@ -1540,7 +1545,9 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
           const NnParams& qg = qs[g];
           in_cap = cudaMemsetAsync(qg.n_rows, 0, sizeof(uint32_t), streams[g]);
           if (in_cap != cudaSuccess) break;
-          nn_step_kernel<<<(qg.slot_end - qg.slot_begin + 3) / 4, 128, smem, streams[g]>>>(p, qg);
+          static const int nn_wpb = [] { const char* v = getenv("AR_NN_WPB"); return v ? atoi(v) : 1; }();
+          if (nn_wpb == 4) nn_step_kernel<4><<<(qg.slot_end - qg.slot_begin + 3) / 4, 128, smem, streams[g]>>>(p, qg);
+          else nn_step_kernel<1><<<qg.slot_end - qg.slot_begin, 32, smem / 4, streams[g]>>>(p, qg);
           in_cap = cudaGetLastError();
           if (in_cap != cudaSuccess) break;
           in_cap = e->eval->forward(qg.rows, qg.n_rows, (int)qg.max_rows, p.games, e->d_maze_tab,
