@@ -155,7 +155,7 @@ __device__ __forceinline__ void load_game(const ar_game_pod* pod, WarpCtx& cx, G
 // (play_game, selfplay.rs:515-598).  search_only: one fresh-tree search per "game"
 // (rust_mcts_search, mcts/bindings.rs:228-304).
 #ifndef AR_MIN_BLOCKS
-#define AR_MIN_BLOCKS 7
+#define AR_MIN_BLOCKS 8
 #endif
 // WPB = warps per block: 4 for a blocking launch; 1 for streaming launches, where a finished warp must give its
 // SM resources back at once (in a 4-warp block the three early finishers idle until the last warp's games end).

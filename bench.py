@@ -5,7 +5,7 @@
 
 Workload (BASELINE.json configs[1]): PyRat 7x7 open maze, 10 cheese, 50 turns, `7x7_rust_tuned`
 (1897 sims, c_puct 0.512, fpu 0.459, force_k 0.103, batch 16), uniform priors, Dirichlet noise 0,
-4096 resident game trees per GPU (one warp each).  One step = one pass of the hot path over one batch of
+4736 resident game trees per GPU (one warp each: 148 SMs x 32 warps; BASELINE names 4096, `--concurrent 4096`).  One step = one pass of the hot path over one batch of
 synthetic games (`--games-per-step` per GPU, default 131072, fresh games every step, played to completion).
 Steps are fed continuously (ar_stream_*: three to eight batches in flight, the next batch's blocks take over the
 SMs as the previous batch's last long games finish), so throughput does not depend on the batch size.
@@ -627,7 +627,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--games-per-step", type=int, default=131072)
-    ap.add_argument("--concurrent", type=int, default=4096)
+    ap.add_argument("--concurrent", type=int, default=4736,
+                    help="resident trees per GPU: 148 SMs x 32 warps (BASELINE names 4096: --concurrent 4096)")
     ap.add_argument("--feed-workers", type=int, default=3, help="processes that build the synthetic batches")
     ap.add_argument("--e2e-keep", type=int, default=4, help="distinct batches kept in host memory for the e2e leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
