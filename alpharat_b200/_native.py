@@ -12,7 +12,7 @@ import os
 from pathlib import Path
 
 AR_ABI_VERSION = 2
-AR_TREE_WARP, AR_TREE_THREAD = 0, 1
+AR_TREE_WARP, AR_TREE_THREAD, AR_TREE_HALF = 0, 1, 2
 AR_MAX_CELLS = 256
 
 AR_OK = 0

@@ -17,6 +17,7 @@
 
 #include "host_tables.hpp"
 #include "mcts_device.cuh"
+#include "mcts_half.cuh"
 #include "nn_api.cuh"
 #include "tree_thread.cuh"
 
@@ -341,6 +342,230 @@ __global__ void __launch_bounds__(32 * WPB, AR_MIN_BLOCKS * 4 / WPB) selfplay_un
   }
 }
 
+
+// =========================================================================================
+// Uniform-prior self-play / search, TWO trees per warp (mcts_half.cuh): each 16-lane half of a warp plays its
+// own games.  The outer control flow is flat — one simulate_batch per loop iteration for whichever state the
+// half is in — so the two halves of a warp meet again at every batch and the hot code (per-level selection,
+// game step, backup) issues once for both trees.
+// =========================================================================================
+__device__ __noinline__ void extract_and_store_h(hw::HalfCtx& cx, const SearchParams& sp, int hl, ar_search_result* out,
+                                                 uint32_t nn, uint32_t term, uint32_t coll, float pol1[5], float pol2[5],
+                                                 uint32_t& total_visits) {
+  ar_search_result res;
+  hw::extract_result(cx, sp, hl, res);
+  res.nn_evals = nn;
+  res.terminals = term;
+  res.collisions = coll;
+#pragma unroll
+  for (int a = 0; a < 5; ++a) { pol1[a] = res.policy_p1[a]; pol2[a] = res.policy_p2[a]; }
+  total_visits = res.total_visits;
+  if (hl == 0) *out = res;
+}
+
+template <int WPB>
+__global__ void __launch_bounds__(32 * WPB, AR_MIN_BLOCKS * 4 / WPB) selfplay_half_kernel(RunParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  int lane = threadIdx.x & 31;
+  asm volatile("" : "+r"(lane));
+  const int hl = lane & 15, half = lane >> 4;
+  const int wib = threadIdx.x >> 5;
+  __shared__ int s_group;
+  __shared__ float s_fpu_tab[36];
+  if (threadIdx.x < 32) {
+    s_fpu_tab[threadIdx.x] = hw::fpu_tab_entry(threadIdx.x / 6, threadIdx.x % 6);
+    if (threadIdx.x < 4) s_fpu_tab[32 + threadIdx.x] = hw::fpu_tab_entry(5, 2 + threadIdx.x);
+  }
+  __syncthreads();
+  int group = blockIdx.x;
+  if (p.slot_bitmap) {  // streaming launches: claim a free group of 2 * WPB tree slots (see selfplay_uniform_kernel)
+    if (threadIdx.x == 0) {
+      const int words = (p.n_groups + 31) / 32;
+      int w = (int)(blockIdx.x % words), got = -1;
+      while (got < 0) {
+        for (int t = 0; t < words && got < 0; ++t) {
+          uint32_t cur = *reinterpret_cast<volatile uint32_t*>(&p.slot_bitmap[w]);
+          while (cur != 0xffffffffu) {
+            const int b = __ffs((int)~cur) - 1;
+            if (w * 32 + b >= p.n_groups) break;
+            const uint32_t old = atomicOr(&p.slot_bitmap[w], 1u << b);
+            if (!(old & (1u << b))) { got = w * 32 + b; break; }
+            cur = old | (1u << b);
+          }
+          w = (w + 1 == words) ? 0 : w + 1;
+        }
+        if (got < 0) __nanosleep(2000);
+      }
+      s_group = got;
+    }
+    __syncthreads();
+    group = s_group;
+  }
+  const int slot = (group * WPB + wib) * 2 + half;
+  const bool live = slot < p.n_slots;
+  const int bslot = live ? slot : 0;  // an idle half binds valid pointers and never uses them
+
+  uint8_t* base = smem + (size_t)(wib * 2 + half) * warp_smem_bytes(p.max_depth, p.batch_cap);
+  hw::HalfCtx cx;
+  cx.hbase = 16 * half;
+  {
+    const float* ft = s_fpu_tab;
+    asm volatile("" : "+l"(ft));
+    __builtin_assume(__isShared(ft));
+    cx.fpu_tab = ft;
+  }
+  cx.bind(base, p.pools + (size_t)bslot * p.pool_nodes, hl, p.max_depth, p.batch_cap);
+  cx.path_buf = p.path_bufs + (size_t)bslot * p.batch_cap * p.path_stride;
+  cx.remap = p.remaps + (size_t)bslot * p.pool_nodes;
+  cx.coll_table = p.coll_table;
+  cx.pool_nodes = p.pool_nodes;
+  cx.path_stride = p.path_stride;
+  cx.epoch = 1;
+  cx.path_nodes = 0;
+  cx.new_nodes = 0;
+  cx.error = 0;
+  cx.node_count = 0;
+  cx.root_claimed = false;
+  const SearchParams sp = p.sp;
+
+  int phase = live ? 0 : 2;  // 0: needs a game, 1: searching, 2: no more games
+  unsigned int gi = 0;
+  GState g;
+  g.cheese = 0; g.p1 = g.p2 = 0; g.mud1 = g.mud2 = 0; g.s1x2 = g.s2x2 = 0;
+  int turn = 0;
+  Rng rng = rng_seed(0);
+  int cheese_available = 0;
+  uint32_t n_pos = 0, remaining = 0, nn = 0, term = 0, coll = 0;
+  unsigned long long tot_sims = 0, tot_nn = 0, tot_term = 0, tot_coll = 0;
+
+  for (;;) {
+    if (__all_sync(FULL, phase == 2)) break;
+    if (phase == 0) {
+      // game_worker_loop (selfplay.rs:609-650): claim the next game index
+      unsigned int x = 0;
+      if (hl == 0) x = atomicAdd(p.next_game, 1u);
+      x = __shfl_sync(__activemask(), x, 0, 16);
+      if (x >= (unsigned)p.n_games) {
+        phase = 2;
+      } else {
+        gi = x;
+        hw::load_game(p.games + gi, cx, g, turn, hl);
+        rng = rng_seed(p.seeds[gi]);
+        cheese_available = __popcll(g.cheese);
+        hw::init_root(cx, g, hl);
+        n_pos = 0;
+        tot_sims = tot_nn = tot_term = tot_coll = 0;
+        remaining = sp.n_sims;
+        nn = term = coll = 0;
+        phase = 1;
+        if (!p.search_only) {
+          uint32_t* co = reinterpret_cast<uint32_t*>(p.summaries[gi].cheese_outcomes);
+          for (int i = hl; i < AR_MAX_CELLS / 4; i += 16) co[i] = 0x02020202u;
+          if (game_over(g, turn, cx.max_turns)) remaining = 0;  // a game that is over before it starts: summary only
+        }
+      }
+    }
+    if (phase == 1) {
+      bool finished = !p.search_only && remaining == 0 && n_pos == 0 && game_over(g, turn, cx.max_turns);
+      if (!finished) {
+        if (remaining > 0) {
+          // ---- one simulate_batch of run_search (search.rs:362-390)
+          const uint32_t bs = min(remaining, sp.batch_size);
+          const uint32_t nn0 = nn, term0 = term;
+          hw::simulate_batch_uniform(cx, sp, rng, g, turn, bs, nn, term, coll, p.coll_table_len, hl);
+          uint32_t produced = (nn - nn0) + (term - term0);
+          produced = produced > 1u ? produced : 1u;
+          remaining = remaining > produced ? remaining - produced : 0u;
+          if (cx.error) phase = 2;
+        }
+        if (phase == 1 && remaining == 0) {
+          // ---- search finished: extract_result, then one self-play move (selfplay.rs:547-565)
+          float pol1[5], pol2[5];
+          ar_position_record* pos = p.positions ? p.positions + (size_t)gi * p.pos_stride : nullptr;
+          ar_search_result* rout = p.search_only ? (p.search_out + gi) : &pos[n_pos].search;
+          uint32_t tv = 0;
+          extract_and_store_h(cx, sp, hl, rout, nn, term, coll, pol1, pol2, tv);
+          if (p.search_only) {
+            phase = 0;
+          } else {
+            tot_sims += tv; tot_nn += nn; tot_term += term; tot_coll += coll;
+            const int a1 = rng_sample_action(rng, pol1);
+            const int a2 = rng_sample_action(rng, pol2);
+            if (hl == 0) {
+              ar_position_record& pr = pos[n_pos];
+              pr.p1_x = (uint8_t)(g.p1 % cx.w); pr.p1_y = (uint8_t)(g.p1 / cx.w);
+              pr.p2_x = (uint8_t)(g.p2 % cx.w); pr.p2_y = (uint8_t)(g.p2 / cx.w);
+              pr.p1_mud = (uint8_t)g.mud1; pr.p2_mud = (uint8_t)g.mud2;
+              pr.action_p1 = (uint8_t)a1; pr.action_p2 = (uint8_t)a2;
+              pr.turn = (uint16_t)turn; pr.reserved = 0;
+              pr.p1_score = 0.5f * (float)g.s1x2; pr.p2_score = 0.5f * (float)g.s2x2;
+              uint32_t* cb = reinterpret_cast<uint32_t*>(pr.cheese);
+              cb[0] = (uint32_t)g.cheese; cb[1] = (uint32_t)(g.cheese >> 32);
+#pragma unroll
+              for (int t = 2; t < 8; ++t) cb[t] = 0;
+            }
+            n_pos += 1;
+            // advance_root maps raw actions through action_to_outcome_idx (tree.rs:283-295)
+            const uint32_t rmeta = cx.pool[0].s[LANE_LINKS].y;
+            const int i = action_to_idx(meta_m1(rmeta), a1), j = action_to_idx(meta_m2(rmeta), a2);
+            const uint32_t child = reinterpret_cast<const uint32_t*>(&cx.pool[0].s[LANE_CHILD])[i * 5 + j];
+            const uint64_t cheese_before = g.cheese;
+            game_step(g, i, j, cx.steptbl());
+            turn += 1;
+            if (hl == 0) credit_cheese(p.summaries[gi], cheese_before, g);
+            hw::hsync();
+            remaining = sp.n_sims;
+            nn = term = coll = 0;
+            if (game_over(g, turn, cx.max_turns)) {
+              finished = true;  // the tree of a finished game is dropped
+            } else if (child != 0) {
+              hw::compact_subtree(cx, child, hl);
+            } else {
+              hw::init_root(cx, g, hl);  // reinit, tree.rs:298-302
+            }
+          }
+        }
+      }
+      if (finished) {
+        if (hl == 0) {
+          ar_game_summary& s = p.summaries[gi];
+          s.game_index = gi;
+          s.n_positions = n_pos;
+          s.final_p1_score = 0.5f * (float)g.s1x2;
+          s.final_p2_score = 0.5f * (float)g.s2x2;
+          s.result = g.s1x2 > g.s2x2 ? 1 : (g.s2x2 > g.s1x2 ? 2 : 0);
+          s.reserved[0] = s.reserved[1] = s.reserved[2] = 0;
+          s.cheese_available = (uint16_t)cheese_available;
+          s.reserved1 = 0;
+          s.total_simulations = tot_sims;
+          s.total_nn_evals = tot_nn;
+          s.total_terminals = tot_term;
+          s.total_collisions = tot_coll;
+          if (p.progress) {
+            atomicAdd_system((unsigned long long*)&p.progress->positions_completed, (unsigned long long)n_pos);
+            atomicAdd_system((unsigned long long*)&p.progress->simulations_completed, tot_sims);
+            atomicAdd_system((unsigned long long*)&p.progress->nn_evals_completed, tot_nn);
+            atomicAdd_system((unsigned int*)&p.progress->games_completed, 1u);
+          }
+          atomicAdd(&p.counters[2], tot_nn);
+          atomicAdd(&p.counters[3], tot_term);
+          atomicAdd(&p.counters[4], (unsigned long long)n_pos);
+          atomicAdd(&p.counters[5], tot_sims);
+        }
+        phase = 0;
+      }
+    }
+  }
+  if (hl == 0 && live) {
+    atomicAdd(&p.counters[0], (unsigned long long)cx.path_nodes);
+    atomicAdd(&p.counters[1], (unsigned long long)cx.new_nodes);
+    if (cx.error) atomicCAS(p.error_flag, 0, (int)cx.error);
+  }
+  if (p.slot_bitmap) {
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAnd(&p.slot_bitmap[group >> 5], ~(1u << (group & 31)));
+  }
+}
 
 // =========================================================================================
 // Uniform-prior self-play / search, thread-per-tree (tree_thread.cuh).  One persistent launch:
@@ -1175,7 +1400,7 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
     return s;
   };
   if (cfg->concurrent_games == 0) return fail(AR_ERR_INVALID_ARG, "concurrent_games must be > 0");
-  if (cfg->tree_engine > AR_TREE_THREAD) return fail(AR_ERR_INVALID_ARG, "tree_engine must be AR_TREE_WARP or AR_TREE_THREAD");
+  if (cfg->tree_engine > AR_TREE_HALF) return fail(AR_ERR_INVALID_ARG, "tree_engine must be AR_TREE_WARP, AR_TREE_THREAD or AR_TREE_HALF");
   if (cfg->max_cells == 0 || cfg->max_cells > AR_MAX_CELLS) return fail(AR_ERR_UNSUPPORTED, "max_cells must be in [1, 256]");
   if (cfg->max_cells > 64 && cfg->tree_engine != AR_TREE_THREAD)
     return fail(AR_ERR_UNSUPPORTED, "boards over 64 cells need tree_engine = AR_TREE_THREAD (the warp engine and the evaluators keep a one-word cheese bitboard)");
@@ -1218,6 +1443,12 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
   CKC(cudaHostGetDevicePointer(&e->d_progress, e->h_progress, 0));
   CKC(cudaFuncSetAttribute(selfplay_uniform_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CKC(cudaFuncSetAttribute(selfplay_uniform_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem / 4));
+  if (2 * smem <= 227 * 1024) {
+    CKC(cudaFuncSetAttribute(selfplay_half_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem)));
+    CKC(cudaFuncSetAttribute(selfplay_half_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem / 2)));
+  } else if (cfg->tree_engine == AR_TREE_HALF) {
+    return fail(AR_ERR_UNSUPPORTED, "max_turns/max_batch_size need too much shared memory for two trees per warp");
+  }
   CKC(cudaFuncSetAttribute(nn_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CKC(cudaFuncSetAttribute(nn_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem / 4));
 #undef CKC
@@ -1439,7 +1670,11 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
     if (s) return s;
   }
   CK(cudaEventRecord(e->cur->ev0, e->cur->stream));
-  if (!nn && !tt_run) {
+  if (!nn && !tt_run && e->cfg.tree_engine == AR_TREE_HALF) {
+    selfplay_half_kernel<4><<<(slots + 7) / 8, 128, 2 * smem, e->cur->stream>>>(p);
+    CK(cudaGetLastError());
+    e->cur->launches += 1;
+  } else if (!nn && !tt_run) {
     selfplay_uniform_kernel<4><<<(slots + 3) / 4, 128, smem, e->cur->stream>>>(p);
     CK(cudaGetLastError());
     e->cur->launches += 1;
@@ -1941,8 +2176,8 @@ ar_status ar_stream_open(ar_engine* e, int32_t n_buffers, int32_t max_games, int
   if (!e) return AR_ERR_INVALID_ARG;
   CK(cudaSetDevice(e->device));
   if (n_buffers < 1 || n_buffers > 8 || max_games < 1 || positions_stride < 1) { e->err = "bad stream shape"; return AR_ERR_INVALID_ARG; }
-  if (e->arch != AR_ARCH_UNIFORM || e->cfg.tree_engine != AR_TREE_WARP) {
-    e->err = "streaming is implemented for the uniform-prior warp engine";
+  if (e->arch != AR_ARCH_UNIFORM || e->cfg.tree_engine == AR_TREE_THREAD) {
+    e->err = "streaming is implemented for the uniform-prior warp engines (AR_TREE_WARP, AR_TREE_HALF)";
     return AR_ERR_UNSUPPORTED;
   }
   ar_stream_close(e);
@@ -2001,9 +2236,11 @@ ar_status ar_stream_launch(ar_engine* e, int32_t buffer, const ar_search_cfg* cf
   p.games = b->d_games; p.seeds = b->d_seeds; p.n_games = b->n_resident;
   p.summaries = b->d_summaries; p.positions = b->d_positions; p.pos_stride = b->resident_stride;
   p.search_only = 0;
+  const bool half_engine = e->cfg.tree_engine == AR_TREE_HALF;
   p.slot_bitmap = e->d_slot_bitmap;
-  p.n_groups = (int)e->n_slots;  // one warp per block: a group is one tree slot
-  p.n_slots = p.n_groups;
+  p.n_groups = half_engine ? (int)e->n_slots / 2 : (int)e->n_slots;  // one warp per block: one tree slot, or two
+  p.n_slots = half_engine ? p.n_groups * 2 : p.n_groups;
+  if (p.n_groups < 1) { e->err = "streaming needs at least one warp's worth of resident trees"; return AR_ERR_INVALID_ARG; }
   p.progress = nullptr;
   b->launches = 0;
   b->t_submit = std::chrono::steady_clock::now();
@@ -2013,8 +2250,13 @@ ar_status ar_stream_launch(ar_engine* e, int32_t buffer, const ar_search_cfg* cf
   CK(cudaEventRecord(b->ev0, b->stream));
   if (b->n_resident > 0) {
     const size_t smem = warp_smem_bytes(e->max_depth, e->batch_cap);
-    const int blocks = std::min(p.n_groups, b->n_resident);
-    selfplay_uniform_kernel<1><<<blocks, 32, smem, b->stream>>>(p);
+    if (half_engine) {
+      const int blocks = std::min(p.n_groups, (b->n_resident + 1) / 2);
+      selfplay_half_kernel<1><<<blocks, 32, 2 * smem, b->stream>>>(p);
+    } else {
+      const int blocks = std::min(p.n_groups, b->n_resident);
+      selfplay_uniform_kernel<1><<<blocks, 32, smem, b->stream>>>(p);
+    }
     CK(cudaGetLastError());
     b->launches = 1;
   }

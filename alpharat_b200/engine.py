@@ -36,7 +36,7 @@ class Engine:
                  max_cells: int = 64, max_turns: int = 64, max_batch_size: int = 16,
                  max_simulations: int = 2048, tree_engine: str | int = "warp") -> None:
         self._lib = N.load_library()
-        te = {"warp": N.AR_TREE_WARP, "thread": N.AR_TREE_THREAD}.get(tree_engine, tree_engine)
+        te = {"warp": N.AR_TREE_WARP, "thread": N.AR_TREE_THREAD, "half": N.AR_TREE_HALF}.get(tree_engine, tree_engine)
         cfg = N.EngineCfg(N.AR_ABI_VERSION, device, concurrent_games, pool_nodes, max_cells,
                           max_turns, max_batch_size, max_simulations, int(te))
         handle = C.c_void_p()

@@ -152,7 +152,7 @@ typedef struct ar_engine_cfg {
   uint32_t max_turns;        /* upper bound on max_turns (depth stack)                 */
   uint32_t max_batch_size;   /* upper bound on ar_search_cfg.batch_size                */
   uint32_t max_simulations;  /* used for pool auto-sizing                              */
-  uint32_t tree_engine;      /* uniform-prior runs: AR_TREE_WARP (default) or AR_TREE_THREAD */
+  uint32_t tree_engine;      /* uniform-prior runs: AR_TREE_WARP (default), AR_TREE_THREAD, AR_TREE_HALF */
 } ar_engine_cfg;
 
 /* Two device engines play the uniform-prior path, bit-identically (both are checked against the
@@ -161,6 +161,7 @@ typedef struct ar_engine_cfg {
  * resident trees; measured slower on B200 (profiles/r2_summary.md), kept as a selectable engine. */
 #define AR_TREE_WARP 0
 #define AR_TREE_THREAD 1
+#define AR_TREE_HALF 2 /* two trees per warp (16 lanes each); same records, pools and results as AR_TREE_WARP */
 
 /* One named f32 tensor of a torch state_dict (host memory). */
 typedef struct ar_tensor_desc {

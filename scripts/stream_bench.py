@@ -1,6 +1,7 @@
 """Continuous-feed probe: K batches of G games through NBUF stream buffers (kernel-only: inputs uploaded by
 ar_stream_submit, no record download), device time from the first launch to the last.  usage: stream_bench.py G K [CONC] [NBUF]"""
 import ctypes as C
+import os
 import sys, time
 sys.path.insert(0, '.')
 from alpharat_b200 import _native as N
@@ -15,7 +16,8 @@ sz = C.sizeof(N.GamePod)
 for off in range(0, G, base):
     C.memmove(C.byref(pods, off * sz), pods0, min(base, G - off) * sz)
 cfg = search_cfg(simulations=1897, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103)
-eng = Engine(concurrent_games=conc, max_turns=50, max_batch_size=16, max_simulations=1897)
+eng = Engine(concurrent_games=conc, max_turns=50, max_batch_size=16, max_simulations=1897,
+             tree_engine=os.environ.get("AR_TREE_ENGINE", "warp"))
 # blocking reference point
 eng.selfplay_upload(pods, list(range(G)))
 st = eng.selfplay_run_resident(cfg)

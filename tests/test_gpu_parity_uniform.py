@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 
 # Both device engines of the uniform-prior path (include/alpharat_cuda.h: AR_TREE_WARP, AR_TREE_THREAD)
 # are held to the same bit-exact bar.
-ENGINES = pytest.mark.parametrize("tree_engine", ["warp", "thread"])
+ENGINES = pytest.mark.parametrize("tree_engine", ["warp", "thread", "half"])
 
 
 def _bytes(x) -> bytes:
