@@ -368,13 +368,15 @@ __global__ void __launch_bounds__(32 * WPB, AR_MIN_BLOCKS * 4 / WPB) selfplay_ha
   extern __shared__ __align__(16) uint8_t smem[];
   int lane = threadIdx.x & 31;
   asm volatile("" : "+r"(lane));
-  const int hl = lane & 15, half = lane >> 4;
+  int hl = lane & 15;
+  const int half = lane >> 4;
   const int wib = threadIdx.x >> 5;
   __shared__ int s_group;
-  __shared__ float s_fpu_tab[36];
+  __shared__ float s_fpu_tab[42];  // [n * 6 + k]: sqrt of the visited prior mass; [36 + n]: the uniform prior 1 / n
   if (threadIdx.x < 32) {
     s_fpu_tab[threadIdx.x] = hw::fpu_tab_entry(threadIdx.x / 6, threadIdx.x % 6);
     if (threadIdx.x < 4) s_fpu_tab[32 + threadIdx.x] = hw::fpu_tab_entry(5, 2 + threadIdx.x);
+    if (threadIdx.x < 6) s_fpu_tab[36 + threadIdx.x] = threadIdx.x ? 1.0f / (float)threadIdx.x : 0.0f;
   }
   __syncthreads();
   int group = blockIdx.x;
@@ -407,14 +409,23 @@ __global__ void __launch_bounds__(32 * WPB, AR_MIN_BLOCKS * 4 / WPB) selfplay_ha
 
   uint8_t* base = smem + (size_t)(wib * 2 + half) * warp_smem_bytes(p.max_depth, p.batch_cap);
   hw::HalfCtx cx;
-  cx.hbase = 16 * half;
   {
     const float* ft = s_fpu_tab;
     asm volatile("" : "+l"(ft));
     __builtin_assume(__isShared(ft));
     cx.fpu_tab = ft;
   }
-  cx.bind(base, p.pools + (size_t)bslot * p.pool_nodes, hl, p.max_depth, p.batch_cap);
+  // The pool of the second half starts 128 bytes into its slot (the allocation carries the slack): both 128-byte
+  // parts of a record stay line-aligned, and bits 3..7 of the lane's record pointer — a register that is live
+  // throughout — spell the lane.  hl and hbase are taken from there, so wherever the compiler re-derives them
+  // under register pressure it is a shift and a mask instead of an S2R round trip (5 % of the stall samples).
+  cx.bind(base, reinterpret_cast<NodeRec*>(reinterpret_cast<uint8_t*>(p.pools + (size_t)bslot * p.pool_nodes) + 128 * half),
+          hl, p.max_depth, p.batch_cap);
+  {
+    const uint32_t lane_bits = ((uint32_t)(uintptr_t)cx.pool_lane >> 3) & 31u;
+    hl = (int)(lane_bits & 15u);
+    cx.hbase = (int)(lane_bits & 16u);
+  }
   cx.path_buf = p.path_bufs + (size_t)bslot * p.batch_cap * p.path_stride;
   cx.remap = p.remaps + (size_t)bslot * p.pool_nodes;
   cx.coll_table = p.coll_table;
@@ -438,8 +449,20 @@ __global__ void __launch_bounds__(32 * WPB, AR_MIN_BLOCKS * 4 / WPB) selfplay_ha
   uint32_t n_pos = 0, remaining = 0, nn = 0, term = 0, coll = 0;
   unsigned long long tot_sims = 0, tot_nn = 0, tot_term = 0, tot_coll = 0;
 
+#ifdef AR_HALF_IDLE  // measurement build: cycles a half spends waiting for the other one at the top of the loop
+  long long t_top = clock64(), t_end = t_top;
+  unsigned long long idle_cycles = 0, total_cycles = 0;
+  cx.idle_pick = cx.idle_backup = 0;
+#endif
   for (;;) {
     if (__all_sync(FULL, phase == 2)) break;
+#ifdef AR_HALF_IDLE
+    {
+      const long long now = clock64();
+      if (phase != 2) { idle_cycles += now - t_end; total_cycles += now - t_top; }
+      t_top = now;
+    }
+#endif
     if (phase == 0) {
       // game_worker_loop (selfplay.rs:609-650): claim the next game index
       unsigned int x = 0;
@@ -547,15 +570,30 @@ __global__ void __launch_bounds__(32 * WPB, AR_MIN_BLOCKS * 4 / WPB) selfplay_ha
             atomicAdd_system((unsigned long long*)&p.progress->nn_evals_completed, tot_nn);
             atomicAdd_system((unsigned int*)&p.progress->games_completed, 1u);
           }
+#ifndef AR_HALF_IDLE
           atomicAdd(&p.counters[2], tot_nn);
           atomicAdd(&p.counters[3], tot_term);
+#endif
           atomicAdd(&p.counters[4], (unsigned long long)n_pos);
           atomicAdd(&p.counters[5], tot_sims);
         }
         phase = 0;
       }
     }
+#ifdef AR_HALF_IDLE
+    t_end = clock64();
+#endif
   }
+#ifdef AR_HALF_IDLE
+  // reported in the path_nodes / new_nodes statistics of this build: waiting cycles / 1024 (end of the descent loop
+  // in the low 32 bits... both sums), total cycles / 1024
+  if (hl == 0 && live) {
+    atomicAdd(&p.counters[2], (unsigned long long)(cx.idle_pick >> 10));
+    atomicAdd(&p.counters[3], (unsigned long long)(cx.idle_backup >> 10));
+  }
+  cx.path_nodes = (uint32_t)(idle_cycles >> 10);
+  cx.new_nodes = (uint32_t)(total_cycles >> 10);
+#endif
   if (hl == 0 && live) {
     atomicAdd(&p.counters[0], (unsigned long long)cx.path_nodes);
     atomicAdd(&p.counters[1], (unsigned long long)cx.new_nodes);
@@ -1579,7 +1617,7 @@ static ar_status ensure_nn_pools(ar_engine* e) {
   uint64_t pn = e->cfg.pool_nodes ? e->cfg.pool_nodes : std::max<uint64_t>(std::min<uint64_t>(e->node_cap, fit), 64);
   pn = std::min<uint64_t>(pn, (1ull << PATH_NODE_BITS) - 1);
   e->pool_nodes = (uint32_t)pn;
-  CK(cudaMalloc(&e->pools, (size_t)e->n_slots * (size_t)pn * sizeof(NodeRec)));
+  CK(cudaMalloc(&e->pools, (size_t)e->n_slots * (size_t)pn * sizeof(NodeRec) + sizeof(NodeRec)));  // + slack: AR_TREE_HALF offsets odd pools
   CK(cudaMalloc(&e->path_bufs, (size_t)e->n_slots * e->batch_cap * e->path_stride * sizeof(uint32_t)));
   CK(cudaMalloc(&e->remaps, (size_t)e->n_slots * pn * sizeof(uint32_t)));
   return AR_OK;

@@ -37,6 +37,9 @@ constexpr int HB_V = 0, HB_TV = 1, HB_LINKS = 2, HB_CHILD = 3;  // B-slot owner 
 struct HalfCtx : WarpCtx {
   int hbase;             // 0 or 16: first lane of this half
   const float* fpu_tab;  // shared memory: sqrt of the visited prior mass under uniform priors, [n * 6 + k]
+#ifdef AR_HALF_IDLE
+  unsigned long long idle_pick, idle_backup;  // measurement build: cycles spent waiting for the other half
+#endif
 };
 
 // sqrt(visited_prior_mass) of compute_fpu (search.rs:120-128) when every prior of the half is 1 / n: the sum
@@ -73,13 +76,24 @@ __device__ __forceinline__ void hsync() {
   check_mask(am);
   __syncwarp(am);
 }
-// maximum over the lane's 8-lane segment (P1 or P2 outcomes of its tree)
-__device__ __forceinline__ uint32_t seg_max(unsigned am, uint32_t key) {
+// maximum over the lane's 8-lane segment (P1 or P2 outcomes of its tree); scores are never NaN and a zero is
+// always +0.0 (the callers add 0.0f), so the float maximum orders them like the reference's comparisons
+__device__ __forceinline__ float seg_max(unsigned am, float x) {
   check_mask(am);
-  key = max(key, __shfl_xor_sync(am, key, 1, 8));
-  key = max(key, __shfl_xor_sync(am, key, 2, 8));
-  key = max(key, __shfl_xor_sync(am, key, 4, 8));
-  return key;
+  x = fmaxf(x, __shfl_xor_sync(am, x, 1, 8));
+  x = fmaxf(x, __shfl_xor_sync(am, x, 2, 8));
+  x = fmaxf(x, __shfl_xor_sync(am, x, 4, 8));
+  return x;
+}
+// prior of the lane's outcome: 1 / n under uniform priors (fpu_tab[36 + n], the value write_new_node stored);
+// the stored priors only at a root that carries Dirichlet noise
+__device__ __forceinline__ float half_prior(const HalfCtx& cx, bool noisy_root, uint2 A, bool valid, int nseg, int seg,
+                                            int o) {
+  if (!noisy_root) return valid ? cx.fpu_tab[36 + nseg] : 0.0f;
+  const unsigned am = __activemask();
+  const int psrc = seg + LANE_PRIOR + ((o < 5 ? o : 0) >> 1);
+  const uint32_t px = hshfl(am, A.x, psrc), py = hshfl(am, A.y, psrc);
+  return valid ? __uint_as_float((o & 1) ? py : px) : 0.0f;
 }
 
 __device__ __forceinline__ void load_rec2(const HalfCtx& cx, uint32_t node, uint2& A, uint2& B) {
@@ -155,18 +169,17 @@ __device__ __forceinline__ int select_single(HalfCtx& cx, const SearchParams& sp
   const int seg = hl & 8, o = hl & 7;
   const int nseg = __popc(seg ? meta_m2(meta) : meta_m1(meta));
   const bool valid = o < nseg;
-  const int psrc = seg + LANE_PRIOR + (o >> 1);
-  const uint32_t px = hshfl(am, A.x, psrc), py = hshfl(am, A.y, psrc);
+  const bool noisy_root = is_root && sp.noise_epsilon > 0.0f;
   const uint32_t v1u = hshfl(am, B.x, HB_V), v2u = hshfl(am, B.y, HB_V);
-  const float prior = valid ? __uint_as_float((o & 1) ? py : px) : 0.0f;
+  const uint32_t unv = ballot16(am, cx, valid && (A.y & VIS_MASK) == 0);
+  const float prior = half_prior(cx, noisy_root, A, valid, nseg, seg, o);
   const float q = valid ? __uint_as_float(A.x) : 0.0f;
   const uint32_t visits = valid ? (A.y & VIS_MASK) : 0u;
   const uint32_t nif = valid ? (A.y >> VIS_BITS) : 0u;
   const float scale = (float)meta_scale(meta);
   const uint32_t cv = tv > 0 ? tv - 1 : 0;
-  const uint32_t unv = ballot16(am, cx, valid && visits == 0);
-  const float fpu = half_fpu(cx, sp, is_root && sp.noise_epsilon > 0.0f, unv, valid, visits, prior,
-                             __uint_as_float(seg ? v2u : v1u), scale, nseg, seg, o);
+  const float fpu = half_fpu(cx, sp, noisy_root, unv, valid, visits, prior, __uint_as_float(seg ? v2u : v1u), scale,
+                             nseg, seg, o);
   const float sqrt_total = sqrt_count<true>((float)(cv > 1u ? cv : 1u));
   const float qv = visits > 0 ? q : fpu;
   const float q_norm = div_guard<true>(qv, scale);
@@ -178,13 +191,12 @@ __device__ __forceinline__ int select_single(HalfCtx& cx, const SearchParams& sp
     score = forced ? 1e20f : score;
   }
   score = valid ? score : NEG_INF;
-  const uint32_t key = fkey(score);
   const unsigned am2 = __activemask();
-  const uint32_t mk = seg_max(am2, key);
-  const uint32_t eq = ballot16(am2, cx, valid && key == mk);
+  const float m = seg_max(am2, score);
+  const uint32_t eq = ballot16(am2, cx, valid && score == m);
   int b1 = __ffs(eq & 0x1fu) - 1, b2 = __ffs((eq >> 8) & 0x1fu) - 1;  // first strict max
   const int first = seg ? b2 : b1;
-  const uint32_t tie = ballot16(am2, cx, valid && o != first && fabsf(score - fkey_inv(mk)) < 1e-12f);
+  const uint32_t tie = ballot16(am2, cx, valid && o != first && fabsf(score - m) < 1e-12f);
   if (tie) break_ties(rng, tie, b1, b2);
   const bool mine = valid && o == (seg ? b2 : b1);
   if (mine) cx.pool_lane[(size_t)node * 32].y = visits | ((nif + 1u) << VIS_BITS);
@@ -209,16 +221,14 @@ __device__ __forceinline__ uint32_t build_level(HalfCtx& cx, const SearchParams&
   const int seg = hl & 8, o = hl & 7;
   const int nseg = seg ? n2 : n1;
   const bool valid = o < nseg;
-  const int psrc = seg + LANE_PRIOR + ((o < 5 ? o : 0) >> 1);
-  const uint32_t px = hshfl(am, A.x, psrc), py = hshfl(am, A.y, psrc);
-  const float prior = valid ? __uint_as_float((o & 1) ? py : px) : 0.0f;
+  const bool noisy_root = is_root && sp.noise_epsilon > 0.0f;
+  const uint32_t unv = ballot16(am, cx, valid && (A.y & VIS_MASK) == 0);
+  const float prior = half_prior(cx, noisy_root, A, valid, nseg, seg, o);
   const float q = valid ? __uint_as_float(A.x) : 0.0f;
   const uint32_t visits = valid ? (A.y & VIS_MASK) : 0u;
   const uint32_t nif = valid ? (A.y >> VIS_BITS) : 0u;
   const float nodeval = seg ? v2 : v1;
-  const uint32_t unv = ballot16(am, cx, valid && visits == 0);
-  const float fpu = half_fpu(cx, sp, is_root && sp.noise_epsilon > 0.0f, unv, valid, visits, prior, nodeval, scale,
-                             nseg, seg, o);
+  const float fpu = half_fpu(cx, sp, noisy_root, unv, valid, visits, prior, nodeval, scale, nseg, seg, o);
   const float sqrt_total = sqrt_count<true>((float)(cv > 1u ? cv : 1u));
   const float qv = visits > 0 ? q : fpu;
   const float q_norm = div_guard<true>(qv, scale);
@@ -236,13 +246,11 @@ __device__ __forceinline__ uint32_t build_level(HalfCtx& cx, const SearchParams&
   while (remaining > 0) {
     float score = NEG_INF;
     if (valid) score = (forced ? 1e20f : q_norm + div_guard<true>(explo_num, 1.0f + (float)ns)) + 0.0f;
-    const uint32_t key = fkey(score);
     const unsigned am1 = __activemask();
-    const uint32_t mk = seg_max(am1, key);
-    const uint32_t eq = ballot16(am1, cx, valid && key == mk);
+    const float m = seg_max(am1, score);
+    const uint32_t eq = ballot16(am1, cx, valid && score == m);
     const int first1 = __ffs(eq & 0x1fu) - 1, first2 = __ffs((eq >> 8) & 0x1fu) - 1;
     const int first = seg ? first2 : first1;
-    const float m = fkey_inv(mk);
     const uint32_t tie = ballot16(am1, cx, valid && o != first && fabsf(score - m) < 1e-12f);
     int b1 = first1, b2 = first2;
     if (tie) break_ties(rng, tie, b1, b2);
@@ -250,22 +258,18 @@ __device__ __forceinline__ uint32_t build_level(HalfCtx& cx, const SearchParams&
     uint32_t k = 1;
     if (remaining > 1) {
       const unsigned am2 = __activemask();
-      const uint32_t key2 = (valid && o != first) ? key : 0u;
-      const uint32_t skey = seg_max(am2, key2);
+      const float second = seg_max(am2, (valid && o != first) ? score : NEG_INF);  // NEG_INF: no other outcome
       const float util = hshfl(am2, q_norm, seg + best);
       const float prior_best = hshfl(am2, prior, seg + best);
       const uint32_t ns_best = hshfl(am2, ns, seg + best);
       uint32_t vtc = 0xffffffffu;
-      if (skey != 0u) {
-        const float second = fkey_inv(skey);
-        if (!(second <= NEG_INF) && !(util >= second)) {
-          const float denom = second - util;
-          if (!(denom <= 0.0f)) {
-            const float n1f = (float)ns_best + 1.0f;
-            const float x = fmaxf(sp.c_puct * prior_best * sqrt_total / denom - n1f + 1.0f, 1.0f);
-            const uint32_t u = f2u_sat(x);
-            vtc = u > 1u ? u : 1u;
-          }
+      if (!(second <= NEG_INF) && !(util >= second)) {
+        const float denom = second - util;
+        if (!(denom <= 0.0f)) {
+          const float n1f = (float)ns_best + 1.0f;
+          const float x = fmaxf(sp.c_puct * prior_best * sqrt_total / denom - n1f + 1.0f, 1.0f);
+          const uint32_t u = f2u_sat(x);
+          vtc = u > 1u ? u : 1u;
         }
       }
       const uint32_t vto = __shfl_xor_sync(__activemask(), vtc, 8, 16);
@@ -678,19 +682,37 @@ __device__ __forceinline__ void simulate_batch_uniform(HalfCtx& cx, const Search
   const uint32_t ci = cx.node_count < coll_len ? cx.node_count : coll_len - 1;
   int collisions_left = (int)cx.coll_table[ci];
   int n_tp = 0;
+#ifdef AR_HALF_IDLE
+  long long t_last = clock64();
+#endif
   while ((uint32_t)n_tp < bs && collisions_left > 0 && cx.error == 0) {
     const uint32_t budget = min((uint32_t)collisions_left, bs - (uint32_t)n_tp);
     const uint32_t c = pick_nodes(cx, sp, rng, root_g, root_turn, budget, n_tp, hl);
     collisions_left -= (int)c;
     coll += c;
+#ifdef AR_HALF_IDLE
+    t_last = clock64();
+#endif
   }
+#ifdef AR_HALF_IDLE
+  __syncwarp(__activemask());
+  cx.idle_pick += clock64() - t_last;
+  t_last = clock64();
+#endif
   if (cx.error) return;
   for (int e = 0; e < n_tp; ++e) {
     const uint8_t kind = cx.tp()[e].kind;
     if (kind == 1) term += 1; else nn += 1;
     if (kind == 0 && cx.tp()[e].node == 0 && sp.noise_epsilon > 0.0f) apply_root_noise(cx, sp, rng, hl);
     backup_entry(cx, e, hl);
+#ifdef AR_HALF_IDLE
+    t_last = clock64();
+#endif
   }
+#ifdef AR_HALF_IDLE
+  __syncwarp(__activemask());
+  cx.idle_backup += clock64() - t_last;
+#endif
 }
 
 __device__ __forceinline__ void load_game(const ar_game_pod* pod, HalfCtx& cx, GState& g, int& turn, int hl) {

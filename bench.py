@@ -5,7 +5,8 @@
 
 Workload (BASELINE.json configs[1]): PyRat 7x7 open maze, 10 cheese, 50 turns, `7x7_rust_tuned`
 (1897 sims, c_puct 0.512, fpu 0.459, force_k 0.103, batch 16), uniform priors, Dirichlet noise 0,
-4736 resident game trees per GPU (one warp each: 148 SMs x 32 warps; BASELINE names 4096, `--concurrent 4096`).  One step = one pass of the hot path over one batch of
+9472 resident game trees per GPU (two per warp, `--tree-engine half`: 148 SMs x 32 warps x 2; `--tree-engine warp` runs 4736,
+one per warp; BASELINE names 4096, `--concurrent 4096`).  One step = one pass of the hot path over one batch of
 synthetic games (`--games-per-step` per GPU, default 131072, fresh games every step, played to completion).
 Steps are fed continuously (ar_stream_*: three to eight batches in flight, the next batch's blocks take over the
 SMs as the previous batch's last long games finish), so throughput does not depend on the batch size.
@@ -126,6 +127,7 @@ def bench_config(args, world: int) -> dict:
     return {
         "workload": WORKLOAD_NAME,
         "concurrent_games_per_gpu": args.concurrent, "games_per_step_per_gpu": args.games_per_step,
+        "tree_engine": args.tree_engine,
         "parallelism": f"games sharded over {world} GPU(s), no data-path collective",
         "l2": "per-GPU node pools (GBs) exceed the 126 MB L2; fresh games every step",
         "simulations_definition": "S_new = nn_evals + terminals (descents performed)",
@@ -411,7 +413,8 @@ def run_cuda(args) -> None:
     n = args.games_per_step
     stride = WORKLOAD["max_turns"]
     eng = Engine(device=local, concurrent_games=args.concurrent, max_turns=stride,
-                 max_batch_size=SEARCH["batch_size"], max_simulations=SEARCH["simulations"])
+                 max_batch_size=SEARCH["batch_size"], max_simulations=SEARCH["simulations"],
+                 tree_engine=args.tree_engine)
     N_BUFFERS = n_buffers(args)
     eng.stream_open(N_BUFFERS, n, stride)
 
@@ -627,8 +630,11 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--games-per-step", type=int, default=131072)
-    ap.add_argument("--concurrent", type=int, default=4736,
-                    help="resident trees per GPU: 148 SMs x 32 warps (BASELINE names 4096: --concurrent 4096)")
+    ap.add_argument("--tree-engine", default="half", choices=["half", "warp"],
+                    help="uniform-prior tree kernel: two trees per warp (default) or one")
+    ap.add_argument("--concurrent", type=int, default=None,
+                    help="resident trees per GPU; default 148 SMs x 32 warps x trees per warp = 9472 (half) / 4736 "
+                         "(warp); BASELINE names 4096: --concurrent 4096")
     ap.add_argument("--feed-workers", type=int, default=3, help="processes that build the synthetic batches")
     ap.add_argument("--e2e-keep", type=int, default=4, help="distinct batches kept in host memory for the e2e leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -640,6 +646,8 @@ def main() -> None:
     ap.add_argument("--no-nn", action="store_true")
     ap.add_argument("--no-nn-parity", action="store_true")
     args = ap.parse_args()
+    if args.concurrent is None:
+        args.concurrent = 9472 if args.tree_engine == "half" else 4736
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -5,6 +5,6 @@
 set -e
 cd "$(dirname "$0")/.."
 C=alpharat_b200/csrc
-nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -fmad=false -DAR_HALF_CHECK -c $C/engine.cu -o /tmp/engine_check.o
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o alpharat_b200/libalpharat_cuda_check.so /tmp/engine_check.o $C/nn_kernels.o $C/nn_symmetric.o $C/nn_cnn.o -lcuda
-echo alpharat_b200/libalpharat_cuda_check.so
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -fmad=false ${AR_DEFS:--DAR_HALF_CHECK} -c $C/engine.cu -o /tmp/engine_check.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ${AR_OUT:-alpharat_b200/libalpharat_cuda_check.so} /tmp/engine_check.o $C/nn_kernels.o $C/nn_symmetric.o $C/nn_cnn.o -lcuda
+echo ${AR_OUT:-alpharat_b200/libalpharat_cuda_check.so}

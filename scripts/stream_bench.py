@@ -27,17 +27,22 @@ print(f"blocking: G={G} device_ms={st.device_ms:.1f} S_new/s={npos * 1897 / st.d
 eng.stream_open(nbuf, G, 50)
 sims = 0
 t0 = time.perf_counter()
-first = last = None
+done = []  # (wall time at which the batch was complete, its simulations)
 for i in range(K + nbuf):
     b = i % nbuf
     if i >= nbuf:
         s = eng.stream_wait(b)
         sims += s.total_nn_evals + s.total_terminals
-        if i - nbuf == 0:
-            pass
+        if os.environ.get("ALPHARAT_CUDA_LIB", "").endswith("_idle.so"):  # -DAR_HALF_IDLE build: cycles / 1024
+            print(f"batch {i - nbuf}: of {s.new_nodes} half-kcycles: waiting at the loop top {s.path_nodes / max(s.new_nodes, 1):.3f}, "
+                  f"after the descents {s.total_nn_evals / max(s.new_nodes, 1):.3f}, after the backups {s.total_terminals / max(s.new_nodes, 1):.3f}", flush=True)
+        done.append((time.perf_counter() - t0, s.total_nn_evals + s.total_terminals))
     if i < K:
         eng.stream_submit(b, pods, cfg, [i * G + j for j in range(G)])
 wall = time.perf_counter() - t0
-ms = eng.stream_elapsed_ms(0, (K - 1) % nbuf) if K > nbuf else None
 print(f"stream: G={G} K={K} nbuf={nbuf} wall_s={wall:.2f} sims={sims} S_new/s(wall)={sims / wall:.3e}", flush=True)
+if K >= 8:  # steady state: completions of the middle batches (the first ones fill the machine, the last ones drain it)
+    lo, hi = 2, K - 3
+    mid = sum(x[1] for x in done[lo + 1:hi + 1])
+    print(f"steady: batches {lo + 1}..{hi}: {mid / (done[hi][0] - done[lo][0]):.3e} S_new/s", flush=True)
 eng.stream_close()

@@ -13,6 +13,9 @@ from test_gpu_parity_uniform import assert_result_equal, compare_selfplay
 
 pytestmark = pytest.mark.gpu
 
+# the two warp-resident engines of the uniform-prior path (one tree per warp, two trees per warp)
+WARP_ENGINES = pytest.mark.parametrize("tree_engine", ["warp", "half"])
+
 
 def test_empty_inputs():
     cfg = search_cfg(simulations=50, batch_size=8)
@@ -22,7 +25,8 @@ def test_empty_inputs():
         assert len(eng.search_batch(pods_array([]), cfg, [])) <= 1
 
 
-def test_ragged_boards_and_lengths_in_one_call(oracle):
+@WARP_ENGINES
+def test_ragged_boards_and_lengths_in_one_call(oracle, tree_engine):
     """Boards of different sizes and max_turns share one call and fewer slots than games."""
     specs = (make_games(6, width=5, height=5, cheese_count=5, max_turns=12)
              + make_games(5, width=7, height=7, cheese_count=10, max_turns=25, first_index=40)
@@ -33,27 +37,29 @@ def test_ragged_boards_and_lengths_in_one_call(oracle):
     n = len(specs)
     cfg = search_cfg(simulations=120, batch_size=8)
     seeds = [3 * i + 1 for i in range(n)]
-    with Engine(concurrent_games=5, max_turns=25, max_batch_size=8, max_simulations=120) as eng:
+    with Engine(concurrent_games=5, max_turns=25, max_batch_size=8, max_simulations=120, tree_engine=tree_engine) as eng:
         gpu = eng.selfplay(pods, cfg, seeds)
     cpu = oracle_selfplay(oracle, pods, cfg, seeds)
     compare_selfplay(gpu, cpu, n)
 
 
-def test_full_bitboard_8x8_and_max_batch(oracle):
+@WARP_ENGINES
+def test_full_bitboard_8x8_and_max_batch(oracle, tree_engine):
     specs = make_games(10, width=8, height=8, cheese_count=20, max_turns=20, first_index=11)
     pods = pods_array(specs)
     cfg = search_cfg(simulations=400, batch_size=64, c_puct=1.1, fpu_reduction=0.3, force_k=1.0,
                      collision_limit_min=4, collision_limit_max=64, collision_scaling_start=20,
                      collision_scaling_end=600, collision_scaling_power=0.7)
     seeds = [100 + i for i in range(10)]
-    with Engine(concurrent_games=10, max_turns=20, max_batch_size=64, max_simulations=400) as eng:
+    with Engine(concurrent_games=10, max_turns=20, max_batch_size=64, max_simulations=400, tree_engine=tree_engine) as eng:
         gpu = eng.selfplay(pods, cfg, seeds)
     cpu = oracle_selfplay(oracle, pods, cfg, seeds)
     compare_selfplay(gpu, cpu, 10)
     assert gpu[3].total_collisions > 0
 
 
-def test_multi_visit_levels_and_tiny_searches(oracle):
+@WARP_ENGINES
+def test_multi_visit_levels_and_tiny_searches(oracle, tree_engine):
     """Collision budgets far above 1 from the first batch (general build_gather_level with visits-to-change
     estimates and parked levels), and searches smaller than one batch."""
     specs = make_games(12, width=7, height=7, cheese_count=10, max_turns=50, first_index=300)
@@ -63,7 +69,7 @@ def test_multi_visit_levels_and_tiny_searches(oracle):
                          collision_limit_min=8, collision_limit_max=200, collision_scaling_start=0,
                          collision_scaling_end=300, collision_scaling_power=1.0)
         seeds = [sims + 13 * i for i in range(12)]
-        with Engine(concurrent_games=12, max_turns=50, max_batch_size=16, max_simulations=sims, pool_nodes=2048) as eng:
+        with Engine(concurrent_games=12, max_turns=50, max_batch_size=16, max_simulations=sims, pool_nodes=2048, tree_engine=tree_engine) as eng:
             out = eng.search_batch(pods, cfg, seeds)
         for i in range(12):
             rc, ref, clean = oracle_search(oracle, pods[i], cfg, seeds[i])
@@ -71,28 +77,30 @@ def test_multi_visit_levels_and_tiny_searches(oracle):
             assert_result_equal(out[i], ref, f"sims={sims} bs={bs} pos {i}")
 
 
-def test_games_that_are_over_before_they_start(oracle):
+@WARP_ENGINES
+def test_games_that_are_over_before_they_start(oracle, tree_engine):
     specs = [GameSpec(5, 5, 10, (0, 0), (4, 4), [(2, 2)], turn=10),          # turn == max_turns
              GameSpec(5, 5, 10, (0, 0), (4, 4), [], turn=0),                  # no cheese
              GameSpec(5, 5, 10, (0, 0), (4, 4), [(2, 2)], p1_score=3.0),      # P1 already has the majority
              GameSpec(5, 5, 10, (1, 1), (3, 3), [(2, 2), (0, 4)])]            # a normal game next to them
     pods = pods_array(specs)
     cfg = search_cfg(simulations=60, batch_size=8)
-    with Engine(concurrent_games=2, max_turns=10, max_batch_size=8, max_simulations=60) as eng:
+    with Engine(concurrent_games=2, max_turns=10, max_batch_size=8, max_simulations=60, tree_engine=tree_engine) as eng:
         gpu = eng.selfplay(pods, cfg, [5, 6, 7, 8])
     cpu = oracle_selfplay(oracle, pods, cfg, [5, 6, 7, 8])
     compare_selfplay(gpu, cpu, 4)
     assert [gpu[0][i].n_positions for i in range(3)] == [0, 0, 0] and gpu[0][3].n_positions > 0
 
 
-def test_results_do_not_depend_on_the_number_of_resident_trees():
+@WARP_ENGINES
+def test_results_do_not_depend_on_the_number_of_resident_trees(tree_engine):
     specs = make_games(24, width=5, height=5, cheese_count=5, max_turns=15)
     pods = pods_array(specs)
     cfg = search_cfg(simulations=80, batch_size=8)
     seeds = list(range(24))
     runs = []
     for conc in (1, 7, 24):
-        with Engine(concurrent_games=conc, max_turns=15, max_batch_size=8, max_simulations=80) as eng:
+        with Engine(concurrent_games=conc, max_turns=15, max_batch_size=8, max_simulations=80, tree_engine=tree_engine) as eng:
             runs.append(eng.selfplay(pods, cfg, seeds))
     compare_selfplay(runs[0], runs[1], 24)
     compare_selfplay(runs[0], runs[2], 24)
@@ -188,7 +196,8 @@ def test_run_cuda_sampling_writes_a_registered_batch(oracle, tmp_path):
     assert got == want
 
 
-def test_streaming_batches_match_blocking_runs(oracle):
+@WARP_ENGINES
+def test_streaming_batches_match_blocking_runs(oracle, tree_engine):
     """ar_stream_*: three batches in flight through two buffers give, game for game, the records of the
     blocking call and of the oracle (launches overlap on the device and share the tree slots)."""
     from conftest import oracle_selfplay
@@ -200,7 +209,7 @@ def test_streaming_batches_match_blocking_runs(oracle):
     for b in range(3):
         specs = make_games(n, width=7, height=7, cheese_count=10, max_turns=50, first_index=7000 + b * n)
         batches.append((pods_array(specs), [900 + b * n + i for i in range(n)]))
-    with Engine(concurrent_games=64, max_turns=50, max_batch_size=16, max_simulations=300) as eng:
+    with Engine(concurrent_games=64, max_turns=50, max_batch_size=16, max_simulations=300, tree_engine=tree_engine) as eng:
         eng.stream_open(2, n, 50)
         eng.stream_submit(0, batches[0][0], cfg, batches[0][1])
         eng.stream_submit(1, batches[1][0], cfg, batches[1][1])
