@@ -300,6 +300,7 @@ __device__ __forceinline__ uint32_t build_level(HalfCtx& cx, const SearchParams&
 }
 
 __device__ __forceinline__ void save_path(HalfCtx& cx, int entry, int depth, uint32_t leaf, int hl) {
+  hsync();  // lane 0 wrote cx.path[0..depth) level by level; one barrier here instead of one per level
   uint32_t* pb = cx.path_buf + (size_t)entry * cx.path_stride;
   for (int j = hl; j <= depth; j += 16) pb[j] = j < depth ? cx.path[j] : leaf;
 }
@@ -388,7 +389,6 @@ __device__ __forceinline__ uint32_t pick_nodes(HalfCtx& cx, const SearchParams& 
       const int rc = (gc.s1x2 - g.s1x2) | ((gc.s2x2 - g.s2x2) << 2);
       const int child_turn = root_turn + d + 1;
       if (hl == 0) cx.path[d] = node | ((uint32_t)f << PATH_NODE_BITS) | ((uint32_t)rc << 28);
-      hsync();
       bool descend = false;
       if (child == 0) {
         if (cx.node_count >= cx.pool_nodes || n_tp >= MAX_BATCH) {
@@ -444,9 +444,8 @@ __device__ __forceinline__ uint32_t pick_nodes(HalfCtx& cx, const SearchParams& 
         n_pend -= 1;
         cs_top = P.cs_begin;
       } else if (hl == 0) {
-        P.cs_cur = (uint16_t)(cur + 1);
+        P.cs_cur = (uint16_t)(cur + 1);  // read again only after the barrier at the top of the next pop
       }
-      hsync();
     }
   }
 }

@@ -580,6 +580,7 @@ def run_cuda(args) -> None:
         tp = ROOT / "profiles" / "traffic_r2.json"
         if tp.exists():
             tj = json.loads(tp.read_text())
+            tj = tj.get(args.tree_engine, tj)  # one capture per tree kernel
             traffic = tj["dram_bytes"] / tj["algorithmic_bytes"] * algo_bytes / max(launches, 1)
         base = cpu_baseline(args.cpu_seconds, os.cpu_count() or 1) if world == 1 and not args.no_cpu else None
         if base:
@@ -605,7 +606,7 @@ def run_cuda(args) -> None:
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_kind": peaks["kind"],
                          "algorithmic_bytes_per_launch": algo_bytes / max(launches, 1),
-                         "kernel": "selfplay_uniform_kernel",
+                         "kernel": "selfplay_half_kernel" if args.tree_engine == "half" else "selfplay_uniform_kernel",
                          "launch_ms_avg": busy_ms / max(launches, 1),
                          "note": "achieved = algorithmic bytes of the timed launches / their device span (launches "
                                  "overlap: the sum of launch durations exceeds the span). The kernel is instruction-issue "

@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/h9_pytest_all.log 2>&1; echo "rc $?" >> gpurun_out/h9_pytest_all.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/h9_smoke.log 2>&1; echo "rc $?" >> gpurun_out/h9_smoke.log
-/usr/bin/time -v timeout 1500 python bench.py --steps 6 --warmup 3 > gpurun_out/h9_bench_n1.json 2> gpurun_out/h9_bench_n1.err; echo "rc $?" >> gpurun_out/h9_bench_n1.err
+nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > gpurun_out/r2_gpu.txt; nproc >> gpurun_out/r2_gpu.txt; lscpu | grep "Model name" >> gpurun_out/r2_gpu.txt
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2f_bench_reference_n1.json 2> gpurun_out/r2f_bench_reference_n1.err
+timeout 1500 python bench.py --steps 8 --warmup 3 > gpurun_out/r2f_bench_n1.json 2> gpurun_out/r2f_bench_n1.err; echo "bench exit $?" >> gpurun_out/r2f_bench_n1.err
+timeout 600 python bench.py --steps 20 --warmup 3 --games-per-step 16384 --no-nn --no-cpu --config5-games 0 > gpurun_out/r2f_bench_n1_16k_k20.json 2> gpurun_out/r2f_bench_n1_16k_k20.err
+timeout 600 python bench.py --steps 20 --warmup 3 --games-per-step 16384 --tree-engine warp --no-nn --no-cpu --config5-games 0 > gpurun_out/r2f_bench_n1_16k_k20_warp.json 2> gpurun_out/r2f_bench_n1_16k_k20_warp.err
