@@ -554,7 +554,7 @@ def run_cuda(args) -> None:
               "records": int(tot5[1].item()),
               "includes": "H2D of the shard, play, device-side record packing, NCCL gather of summaries + position "
                           "records to rank 0 (device to device), D2H on rank 0, all-reduce of the stats vector",
-              "residual": "a fixed total leaves 65536/N games per GPU for 4096 resident trees: the run ends with the "
+              "residual": "a fixed total leaves 65536/N games per GPU for the resident trees: the run ends with the "
                           "tail of its longest games (no next batch to overlap), the collective is a few ms"}
 
     # ---- max over ranks, sum of work -------------------------------------------------------------------------
