@@ -57,6 +57,9 @@ class CudaMCTSConfig(_SearchFields):
     concurrent_games: int = 4096
     pool_nodes: int = 0  # 0 = auto: max_turns * simulations + 2 nodes per tree when that fits in 70 % of free HBM
     seed: int | None = None
+    # uniform-prior self-play kernel: "warp" (a warp per tree), "half" (two trees per warp: the fastest once
+    # concurrent_games is about 148 SMs x 32 warps x 2 = 9472 and the run has several games per tree) or "thread"
+    tree_engine: Literal["warp", "half", "thread"] = "warp"
 
     def build_searcher(self, checkpoint: str | None = None, device: str = "cuda"):
         from .searcher import CudaSearcher

@@ -121,7 +121,7 @@ def self_play_kwargs(game: Any, mcts: Any, num_games: int) -> dict[str, Any]:
         kwargs["maze_symmetric"] = game.maze.symmetric
     for f in _SEARCH_FIELDS:
         kwargs[f] = getattr(mcts, f)
-    for f in ("concurrent_games", "pool_nodes", "seed"):  # CudaMCTSConfig only
+    for f in ("concurrent_games", "pool_nodes", "seed", "tree_engine"):  # CudaMCTSConfig only
         if hasattr(mcts, f):
             kwargs[f] = getattr(mcts, f)
     return kwargs

@@ -262,6 +262,7 @@ def test_run_cuda_sampling_batch_protocol(oracle, tmp_path):
     assert len(list((batch_dir / "games").glob("bundle_*.npz"))) == 2
     assert seen["output_dir"] == str(batch_dir / "games") and seen["device"] == 0
     assert (seen["concurrent_games"], seen["seed"], seen["simulations"], seen["maze_type"]) == (64, 11, 40, "open")
+    assert seen["tree_engine"] == "warp"  # CudaMCTSConfig default; "half" = two trees per warp
     assert "wall_density" not in seen and seen["cheese_symmetric"] is True and seen["positions"] == "corners"
     assert m.total_games == 6 and m.total_positions > 0 and m.elapsed_seconds == 0.5
     assert m.games_per_second == 12.0 and 0 < m.cheese_utilization <= 1 and m.avg_turns == m.total_positions / 6
