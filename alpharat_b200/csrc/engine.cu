@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(32 * WPB, AR_MIN_BLOCKS * 4 / WPB) selfplay_ha
   const bool live = slot < p.n_slots;
   const int bslot = live ? slot : 0;  // an idle half binds valid pointers and never uses them
 
-  uint8_t* base = smem + (size_t)(wib * 2 + half) * warp_smem_bytes(p.max_depth, p.batch_cap);
+  uint8_t* base = smem + (size_t)(wib * 2 + half) * hw::half_smem_bytes(p.max_depth, p.batch_cap);
   hw::HalfCtx cx;
   {
     const float* ft = s_fpu_tab;
@@ -419,8 +419,8 @@ __global__ void __launch_bounds__(32 * WPB, AR_MIN_BLOCKS * 4 / WPB) selfplay_ha
   // parts of a record stay line-aligned, and bits 3..7 of the lane's record pointer — a register that is live
   // throughout — spell the lane.  hl and hbase are taken from there, so wherever the compiler re-derives them
   // under register pressure it is a shift and a mask instead of an S2R round trip (5 % of the stall samples).
-  cx.bind(base, reinterpret_cast<NodeRec*>(reinterpret_cast<uint8_t*>(p.pools + (size_t)bslot * p.pool_nodes) + 128 * half),
-          hl, p.max_depth, p.batch_cap);
+  cx.bind_half(base, reinterpret_cast<NodeRec*>(reinterpret_cast<uint8_t*>(p.pools + (size_t)bslot * p.pool_nodes) + 128 * half),
+               hl, p.max_depth, p.batch_cap);
   {
     const uint32_t lane_bits = ((uint32_t)(uintptr_t)cx.pool_lane >> 3) & 31u;
     hl = (int)(lane_bits & 15u);
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(32 * WPB, AR_MIN_BLOCKS * 4 / WPB) selfplay_ha
             const int i = action_to_idx(meta_m1(rmeta), a1), j = action_to_idx(meta_m2(rmeta), a2);
             const uint32_t child = reinterpret_cast<const uint32_t*>(&cx.pool[0].s[LANE_CHILD])[i * 5 + j];
             const uint64_t cheese_before = g.cheese;
-            game_step(g, i, j, cx.steptbl());
+            game_step<hw::H_STRIDE>(g, i, j, cx.steptbl());
             turn += 1;
             if (hl == 0) credit_cheese(p.summaries[gi], cheese_before, g);
             hw::hsync();
@@ -1481,9 +1481,10 @@ ar_status ar_engine_create(const ar_engine_cfg* cfg, ar_engine** out) {
   CKC(cudaHostGetDevicePointer(&e->d_progress, e->h_progress, 0));
   CKC(cudaFuncSetAttribute(selfplay_uniform_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CKC(cudaFuncSetAttribute(selfplay_uniform_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem / 4));
-  if (2 * smem <= 227 * 1024) {
-    CKC(cudaFuncSetAttribute(selfplay_half_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem)));
-    CKC(cudaFuncSetAttribute(selfplay_half_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem / 2)));
+  const size_t hsmem = 2 * hw::half_smem_bytes(e->max_depth, e->batch_cap);  // one warp of the two-trees-per-warp kernel
+  if (4 * hsmem <= 227 * 1024) {
+    CKC(cudaFuncSetAttribute(selfplay_half_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * hsmem)));
+    CKC(cudaFuncSetAttribute(selfplay_half_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
   } else if (cfg->tree_engine == AR_TREE_HALF) {
     return fail(AR_ERR_UNSUPPORTED, "max_turns/max_batch_size need too much shared memory for two trees per warp");
   }
@@ -1709,7 +1710,7 @@ static ar_status launch_and_wait(ar_engine* e, RunParams& p, ar_progress* user_p
   }
   CK(cudaEventRecord(e->cur->ev0, e->cur->stream));
   if (!nn && !tt_run && e->cfg.tree_engine == AR_TREE_HALF) {
-    selfplay_half_kernel<4><<<(slots + 7) / 8, 128, 2 * smem, e->cur->stream>>>(p);
+    selfplay_half_kernel<4><<<(slots + 7) / 8, 128, 8 * hw::half_smem_bytes(e->max_depth, e->batch_cap), e->cur->stream>>>(p);
     CK(cudaGetLastError());
     e->cur->launches += 1;
   } else if (!nn && !tt_run) {
@@ -2290,7 +2291,7 @@ ar_status ar_stream_launch(ar_engine* e, int32_t buffer, const ar_search_cfg* cf
     const size_t smem = warp_smem_bytes(e->max_depth, e->batch_cap);
     if (half_engine) {
       const int blocks = std::min(p.n_groups, (b->n_resident + 1) / 2);
-      selfplay_half_kernel<1><<<blocks, 32, 2 * smem, b->stream>>>(p);
+      selfplay_half_kernel<1><<<blocks, 32, 2 * hw::half_smem_bytes(e->max_depth, e->batch_cap), b->stream>>>(p);
     } else {
       const int blocks = std::min(p.n_groups, b->n_resident);
       selfplay_uniform_kernel<1><<<blocks, 32, smem, b->stream>>>(p);

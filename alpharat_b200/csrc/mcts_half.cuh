@@ -34,9 +34,38 @@ namespace hw {
 
 constexpr int HB_V = 0, HB_TV = 1, HB_LINKS = 2, HB_CHILD = 3;  // B-slot owner lanes: slot 16 + hl
 
+// Shared memory of one half: [move table 64 x 5 x 2 = 640][maze costs 256][tp: bc x 8][path: max_depth x 4]
+// [pend: bc x 32][cstack: (bc + 1) x 8] — the layout of mcts_device.cuh with a five-wide move table (a cell has at
+// most five outcomes) and without the leaf states of the NN-guided kernel: 1880 instead of 2520 bytes at batch 16 /
+// 50 turns.  With the per-block reserve that takes the one-warp blocks of a streaming launch from 200 KB to 159 KB
+// per SM, i.e. from the 228 KB shared-memory carve-out to the 164 KB one: 92 KB of L1 instead of 28 (+1.4 % in an
+// A/B; loading the records around the L1 costs 5 %, profiles/r2_half_engine_experiments.log).
+constexpr int H_STRIDE = 5, H_MAZE = 640, H_TP = 896;
+__host__ __device__ inline size_t half_smem_bytes(uint32_t max_depth, uint32_t batch_cap) {
+  size_t b = H_TP + (size_t)batch_cap * 8;
+  b += ((size_t)max_depth * 4 + 15) & ~(size_t)15;
+  b += (size_t)batch_cap * 32;
+  b += (size_t)(batch_cap + 1) * 8;
+  return (b + 15) & ~(size_t)15;
+}
+
 struct HalfCtx : WarpCtx {
   int hbase;             // 0 or 16: first lane of this half
   const float* fpu_tab;  // shared memory: sqrt of the visited prior mass under uniform priors, [n * 6 + k]
+  // these hide the WarpCtx accessors (same names, this half's layout)
+  __device__ __forceinline__ const uint16_t* steptbl() const { return reinterpret_cast<const uint16_t*>(sm); }
+  __device__ __forceinline__ uint8_t* maze() const { return sm + H_MAZE; }
+  __device__ __forceinline__ TpEntry* tp() const { return reinterpret_cast<TpEntry*>(sm + H_TP); }
+  __device__ __forceinline__ PendLevel* pend() const {
+    return reinterpret_cast<PendLevel*>(reinterpret_cast<uint8_t*>(path) + (((size_t)max_depth * 4 + 15) & ~(size_t)15));
+  }
+  __device__ __forceinline__ ChildEnt* cstack() const { return reinterpret_cast<ChildEnt*>(pend() + batch_cap); }
+  __device__ __forceinline__ void bind_half(uint8_t* base, NodeRec* pool_, int lane, uint32_t max_depth_, uint32_t batch_cap_) {
+    bind(base, pool_, lane, max_depth_, batch_cap_);
+    path = reinterpret_cast<uint32_t*>(sm + H_TP + (size_t)batch_cap_ * 8);
+    asm volatile("" : "+l"(path));
+    __builtin_assume(__isShared(path));
+  }
 #ifdef AR_HALF_IDLE
   unsigned long long idle_pick, idle_backup;  // measurement build: cycles spent waiting for the other half
 #endif
@@ -385,7 +414,7 @@ __device__ __forceinline__ uint32_t pick_nodes(HalfCtx& cx, const SearchParams& 
       uint2 cA = make_uint2(0, 0), cB = make_uint2(0, 0);
       if (child != 0) load_rec2(cx, child, cA, cB);
       GState gc = g;
-      game_step(gc, a1, a2, cx.steptbl());
+      game_step<H_STRIDE>(gc, a1, a2, cx.steptbl());
       const int rc = (gc.s1x2 - g.s1x2) | ((gc.s2x2 - g.s2x2) << 2);
       const int child_turn = root_turn + d + 1;
       if (hl == 0) cx.path[d] = node | ((uint32_t)f << PATH_NODE_BITS) | ((uint32_t)rc << 28);
@@ -724,8 +753,8 @@ __device__ __forceinline__ void load_game(const ar_game_pod* pod, HalfCtx& cx, G
     reinterpret_cast<uint32_t*>(cx.maze())[i] =
         (i < cx.cells) ? reinterpret_cast<const uint32_t*>(pod->move_cost)[i] : 0u;
   uint16_t* tbl = const_cast<uint16_t*>(cx.steptbl());
-  for (int i = hl; i < 64 * 8; i += 16) {
-    const int c = i >> 3, oi = i & 7;
+  for (int i = hl; i < 64 * H_STRIDE; i += 16) {
+    const int c = i / H_STRIDE, oi = i - c * H_STRIDE;
     uint32_t e = (uint32_t)c;
     if (c < cx.cells) {
       int a = -1, seen = 0;
