@@ -36,7 +36,7 @@ constexpr int HB_V = 0, HB_TV = 1, HB_LINKS = 2, HB_CHILD = 3;  // B-slot owner 
 
 // Shared memory of one half: [move table 64 x 5 x 2 = 640][maze costs 256][tp: bc x 8][path: max_depth x 4]
 // [pend: bc x 32][cstack: (bc + 1) x 8] — the layout of mcts_device.cuh with a five-wide move table (a cell has at
-// most five outcomes) and without the leaf states of the NN-guided kernel: 1880 instead of 2520 bytes at batch 16 /
+// most five outcomes) and without the leaf states of the NN-guided kernel: 1888 instead of 2520 bytes at batch 16 /
 // 50 turns.  With the per-block reserve that takes the one-warp blocks of a streaming launch from 200 KB to 159 KB
 // per SM, i.e. from the 228 KB shared-memory carve-out to the 164 KB one: 92 KB of L1 instead of 28 (+1.4 % in an
 // A/B; loading the records around the L1 costs 5 %, profiles/r2_half_engine_experiments.log).
