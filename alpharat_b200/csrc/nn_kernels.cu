@@ -313,20 +313,30 @@ int MlpModel::load(const ar_tensor_desc* t, int n, int width, int height, std::s
   obs_dim = 7 * width * height + 6;
   const ar_tensor_desc* w1d = find_tensor(t, n, "trunk.0.weight");
   if (!w1d || w1d->ndim != 2) { err = "trunk.0.weight missing"; return AR_ERR_INVALID_ARG; }
-  if (w1d->shape[0] != 256) { err = "only hidden_dim = 256 is supported by the fused MLP kernel"; return AR_ERR_UNSUPPORTED; }
+  // The kernel computes 256 hidden columns.  A narrower trunk (hidden_dim < 256) runs zero-padded: the extra units
+  // have zero weights and zero bias, so they are exactly 0 after the ReLU and add exactly 0 downstream.
+  const int hid = (int)w1d->shape[0];
+  if (hid < 1 || hid > 256) { err = "hidden_dim must be in [1, 256] for the fused MLP kernel (narrower trunks are zero-padded to its 256 columns), got " + std::to_string(hid); return AR_ERR_UNSUPPORTED; }
   if (w1d->shape[1] != obs_dim) { err = "trunk.0.weight does not match obs_dim " + std::to_string(obs_dim); return AR_ERR_INVALID_ARG; }
   k1_blocks = (obs_dim + KB - 1) / KB;
   if (k1_blocks > 6) { err = "obs_dim > 384 does not fit the shared-memory budget of this kernel"; return AR_ERR_UNSUPPORTED; }
-  std::vector<float> W1, b1, W2, b2, Wp1, bp1, Wp2, bp2, Wv, bv;
-  if (!fold_linear_bn(t, n, "trunk.0", "trunk.1", 256, obs_dim, W1, b1, err)) return AR_ERR_INVALID_ARG;
-  if (!fold_linear_bn(t, n, "trunk.4", "trunk.5", 256, 256, W2, b2, err)) return AR_ERR_INVALID_ARG;
-  if (!fold_linear_bn(t, n, "policy_p1_head", "", 5, 256, Wp1, bp1, err)) return AR_ERR_INVALID_ARG;
-  if (!fold_linear_bn(t, n, "policy_p2_head", "", 5, 256, Wp2, bp2, err)) return AR_ERR_INVALID_ARG;
-  if (!fold_linear_bn(t, n, "value_head", "", 2, 256, Wv, bv, err)) return AR_ERR_INVALID_ARG;
+  std::vector<float> W1h, b1h, W2h, b2h, Wp1, bp1, Wp2, bp2, Wv, bv;
+  if (!fold_linear_bn(t, n, "trunk.0", "trunk.1", hid, obs_dim, W1h, b1h, err)) return AR_ERR_INVALID_ARG;
+  if (!fold_linear_bn(t, n, "trunk.4", "trunk.5", hid, hid, W2h, b2h, err)) return AR_ERR_INVALID_ARG;
+  if (!fold_linear_bn(t, n, "policy_p1_head", "", 5, hid, Wp1, bp1, err)) return AR_ERR_INVALID_ARG;
+  if (!fold_linear_bn(t, n, "policy_p2_head", "", 5, hid, Wp2, bp2, err)) return AR_ERR_INVALID_ARG;
+  if (!fold_linear_bn(t, n, "value_head", "", 2, hid, Wv, bv, err)) return AR_ERR_INVALID_ARG;
+  std::vector<float> W1((size_t)256 * obs_dim, 0.0f), b1(256, 0.0f), W2((size_t)256 * 256, 0.0f), b2(256, 0.0f);
   std::vector<float> W3((size_t)16 * 256, 0.0f), b3(16, 0.0f);
-  memcpy(&W3[0], Wp1.data(), 5 * 256 * 4);
-  memcpy(&W3[5 * 256], Wp2.data(), 5 * 256 * 4);
-  memcpy(&W3[10 * 256], Wv.data(), 2 * 256 * 4);
+  memcpy(W1.data(), W1h.data(), (size_t)hid * obs_dim * 4);
+  memcpy(b1.data(), b1h.data(), (size_t)hid * 4);
+  memcpy(b2.data(), b2h.data(), (size_t)hid * 4);
+  for (int r = 0; r < hid; ++r) memcpy(&W2[(size_t)r * 256], &W2h[(size_t)r * hid], (size_t)hid * 4);
+  for (int j = 0; j < 5; ++j) {
+    memcpy(&W3[(size_t)j * 256], &Wp1[(size_t)j * hid], (size_t)hid * 4);
+    memcpy(&W3[(size_t)(5 + j) * 256], &Wp2[(size_t)j * hid], (size_t)hid * 4);
+  }
+  for (int j = 0; j < 2; ++j) memcpy(&W3[(size_t)(10 + j) * 256], &Wv[(size_t)j * hid], (size_t)hid * 4);
   for (int i = 0; i < 5; ++i) { b3[i] = bp1[i]; b3[5 + i] = bp2[i]; }
   b3[10] = bv[0]; b3[11] = bv[1];
   std::vector<uint8_t> i1 = swizzled_image(W1, 256, obs_dim, 256, k1_blocks);

@@ -77,6 +77,35 @@ def test_mlp_forward_matches_reference(n):
     assert (v1 >= 0).all() and (v2 >= 0).all()
 
 
+@pytest.mark.parametrize("hidden", [128, 64, 200])
+def test_mlp_narrower_trunks_run_zero_padded(hidden):
+    """hidden_dim < 256: the loader pads the trunk to the kernel's 256 columns with zero
+    weights and biases, which leaves the outputs unchanged.  128: against the real reference's PyRatMLP(hidden_dim=128)
+    golden; the other widths against the fp32 / bf16 restatements (validated against the reference at 128 and 256)."""
+    n = 300
+    base = random_positions(96, 7, 7, seed=123)
+    specs = [base[i % 96] for i in range(n)]
+    idx = np.arange(n) % 96
+    sd = make_mlp_state_dict(1, 349, hidden=hidden)
+    obs = np.load(GOLD / "flat_builder_7x7.npz")["obs"]
+    with Engine(concurrent_games=4, max_turns=120) as eng:
+        eng.load_weights(N.AR_ARCH_MLP, 7, 7, sd)
+        out = eng.nn_forward(pods_array(specs))
+    if hidden == 128:
+        gold = np.load(GOLD / "mlp_7x7_h128.npz")
+        ref = (gold["policy_p1"][idx], gold["policy_p2"][idx], gold["value_p1"][idx], gold["value_p2"][idx])
+        _check_vs_fp32(out, ref, 2e-2, 3e-2, "mlp hidden 128 vs reference golden")
+    _check_vs_fp32(out, mlp_forward(sd, obs[idx]), 2e-2, 3e-2, f"mlp hidden {hidden} fp32")
+    _check_vs_fp32(out, mlp_forward(sd, obs[idx], emulate_bf16=True), 2e-3, 4e-3, f"mlp hidden {hidden} bf16 restatement")
+
+
+def test_mlp_wider_than_256_fails_loudly():
+    sd = make_mlp_state_dict(1, 349, hidden=512)
+    with Engine(concurrent_games=4, max_turns=120) as eng:
+        with pytest.raises(RuntimeError, match="hidden_dim"):
+            eng.load_weights(N.AR_ARCH_MLP, 7, 7, sd)
+
+
 @pytest.mark.parametrize("w,h,n", [(5, 5, 300), (4, 3, 70), (6, 5, 129)])
 def test_mlp_forward_small_boards(w, h, n):
     """Boards whose observation needs fewer K-blocks than the 256-wide hidden layers (5x5: 3, 4x3: 2): the operand

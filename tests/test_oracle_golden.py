@@ -61,6 +61,16 @@ def test_mlp_restatement_matches_reference_model():
     assert np.abs(v1 - g["value_p1"]).max() <= 1e-5 and np.abs(v2 - g["value_p2"]).max() <= 1e-5
 
 
+def test_mlp_restatement_matches_reference_model_hidden_128():
+    """The same for PyRatMLP(hidden_dim=128): the golden the zero-padded CUDA evaluator is held to."""
+    sd = make_mlp_state_dict(1, 349, hidden=128)
+    obs = np.load(GOLD / "flat_builder_7x7.npz")["obs"]
+    g = np.load(GOLD / "mlp_7x7_h128.npz")
+    p1, p2, v1, v2 = mlp_forward(sd, obs)
+    assert np.abs(p1 - g["policy_p1"]).max() <= 1e-5 and np.abs(p2 - g["policy_p2"]).max() <= 1e-5
+    assert np.abs(v1 - g["value_p1"]).max() <= 1e-5 and np.abs(v2 - g["value_p2"]).max() <= 1e-5
+
+
 def _golden_obs(oracle, w, h):
     if (w, h) == (7, 7):
         return np.load(GOLD / "flat_builder_7x7.npz")["obs"]
