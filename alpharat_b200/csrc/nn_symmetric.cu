@@ -325,24 +325,41 @@ struct Model : LeafEvaluator {
     const int shared_dim = 5 * S + 1, player_dim = S + 2;
     const ar_tensor_desc* d0 = find_tensor(t, n, "shared_encoder.0.weight");
     if (!d0 || d0->ndim != 2) { err = "shared_encoder.0.weight missing (not a SymmetricMLP state_dict)"; return AR_ERR_INVALID_ARG; }
-    if (d0->shape[0] != 256) { err = "only hidden_dim = 256 is supported by the fused SymmetricMLP kernel"; return AR_ERR_UNSUPPORTED; }
+    // The kernel computes 256 hidden columns per stage.  A narrower model (hidden_dim H < 256) runs zero-padded: the
+    // extra units have zero weights and zero bias, are exactly 0 after their ReLU and add exactly 0 downstream.  The
+    // concatenations keep the kernel's strides: cat(shared, p_i) lives at columns [0, H) and [256, 256 + H).
+    const int H = (int)d0->shape[0];
+    if (H < 1 || H > 256) { err = "hidden_dim must be in [1, 256] for the fused SymmetricMLP kernel (narrower models are zero-padded to its 256 columns), got " + std::to_string(H); return AR_ERR_UNSUPPORTED; }
     if (d0->shape[1] != shared_dim) { err = "shared_encoder.0.weight does not match the board size"; return AR_ERR_INVALID_ARG; }
     const int ks = (shared_dim + KB - 1) / KB;
     if (ks > 4 || player_dim > KB) { err = "board too large for the fused SymmetricMLP kernel (needs 5S+1 <= 256, S+2 <= 64)"; return AR_ERR_UNSUPPORTED; }
-    std::vector<float> Ws, bs, Wp, bp, Wt1, bt1, Wt2, bt2, Wpol, bpol, Wval, bval;
-    if (!fold_linear_bn(t, n, "shared_encoder.0", "shared_encoder.1", 256, shared_dim, Ws, bs, err)) return AR_ERR_INVALID_ARG;
-    if (!fold_linear_bn(t, n, "player_encoder.0", "player_encoder.1", 256, player_dim, Wp, bp, err)) return AR_ERR_INVALID_ARG;
-    if (!fold_linear_bn(t, n, "trunk.0", "trunk.1", 256, 512, Wt1, bt1, err)) return AR_ERR_INVALID_ARG;
-    if (!fold_linear_bn(t, n, "trunk.4", "trunk.5", 256, 256, Wt2, bt2, err)) return AR_ERR_INVALID_ARG;
-    if (!fold_linear_bn(t, n, "policy_head", "", 5, 512, Wpol, bpol, err)) return AR_ERR_INVALID_ARG;
-    if (!fold_linear_bn(t, n, "value_head", "", 1, 512, Wval, bval, err)) return AR_ERR_INVALID_ARG;
+    std::vector<float> Wsh, bsh, Wph, bph, Wt1h, bt1h, Wt2h, bt2h, Wpol, bpol, Wval, bval;
+    if (!fold_linear_bn(t, n, "shared_encoder.0", "shared_encoder.1", H, shared_dim, Wsh, bsh, err)) return AR_ERR_INVALID_ARG;
+    if (!fold_linear_bn(t, n, "player_encoder.0", "player_encoder.1", H, player_dim, Wph, bph, err)) return AR_ERR_INVALID_ARG;
+    if (!fold_linear_bn(t, n, "trunk.0", "trunk.1", H, 2 * H, Wt1h, bt1h, err)) return AR_ERR_INVALID_ARG;
+    if (!fold_linear_bn(t, n, "trunk.4", "trunk.5", H, H, Wt2h, bt2h, err)) return AR_ERR_INVALID_ARG;
+    if (!fold_linear_bn(t, n, "policy_head", "", 5, 2 * H, Wpol, bpol, err)) return AR_ERR_INVALID_ARG;
+    if (!fold_linear_bn(t, n, "value_head", "", 1, 2 * H, Wval, bval, err)) return AR_ERR_INVALID_ARG;
+    std::vector<float> Ws((size_t)256 * shared_dim, 0.0f), bs(256, 0.0f), Wp((size_t)256 * player_dim, 0.0f), bp(256, 0.0f);
+    std::vector<float> Wt1((size_t)256 * 512, 0.0f), bt1(256, 0.0f), Wt2((size_t)256 * 256, 0.0f), bt2(256, 0.0f);
+    memcpy(Ws.data(), Wsh.data(), (size_t)H * shared_dim * 4);
+    memcpy(Wp.data(), Wph.data(), (size_t)H * player_dim * 4);
+    memcpy(bs.data(), bsh.data(), (size_t)H * 4);
+    memcpy(bp.data(), bph.data(), (size_t)H * 4);
+    memcpy(bt1.data(), bt1h.data(), (size_t)H * 4);
+    memcpy(bt2.data(), bt2h.data(), (size_t)H * 4);
+    for (int r = 0; r < H; ++r) {
+      memcpy(&Wt1[(size_t)r * 512], &Wt1h[(size_t)r * 2 * H], (size_t)H * 4);
+      memcpy(&Wt1[(size_t)r * 512 + 256], &Wt1h[(size_t)r * 2 * H + H], (size_t)H * 4);
+      memcpy(&Wt2[(size_t)r * 256], &Wt2h[(size_t)r * H], (size_t)H * 4);
+    }
     std::vector<float> Wh((size_t)16 * 256, 0.0f);
     for (int j = 0; j < 5; ++j) {
-      memcpy(&Wh[(size_t)j * 256], &Wpol[(size_t)j * 512], 256 * 4);
-      memcpy(&Wh[(size_t)(6 + j) * 256], &Wpol[(size_t)j * 512 + 256], 256 * 4);
+      memcpy(&Wh[(size_t)j * 256], &Wpol[(size_t)j * 2 * H], (size_t)H * 4);
+      memcpy(&Wh[(size_t)(6 + j) * 256], &Wpol[(size_t)j * 2 * H + H], (size_t)H * 4);
     }
-    memcpy(&Wh[(size_t)5 * 256], &Wval[0], 256 * 4);
-    memcpy(&Wh[(size_t)11 * 256], &Wval[256], 256 * 4);
+    memcpy(&Wh[(size_t)5 * 256], &Wval[0], (size_t)H * 4);
+    memcpy(&Wh[(size_t)11 * 256], &Wval[H], (size_t)H * 4);
     std::vector<uint8_t> img = swizzled_image(Ws, 256, shared_dim, 256, ks);
     const size_t o_wp = img.size();
     std::vector<uint8_t> i2 = swizzled_image(Wp, 256, player_dim, 256, 1);

@@ -154,6 +154,26 @@ def test_symmetric_forward_matches_reference(w, h, n):
                    f"symmetric {w}x{h} n={n}")
 
 
+@pytest.mark.parametrize("hidden", [128, 96])
+def test_symmetric_narrower_models_run_zero_padded(hidden):
+    """hidden_dim < 256: the loader pads every stage to the kernel's 256 columns (cat(shared, p_i) keeps the kernel's
+    stride: columns [0, H) and [256, 256 + H)).  128: against the real reference's SymmetricMLP(hidden_dim=128) golden;
+    96: against the fp32 restatement (validated against the reference at 128 and 256)."""
+    n = 200
+    specs, nb = _positions(7, 7, n)
+    idx = np.arange(n) % nb
+    sd = make_symmetric_state_dict(4, 7, 7, hidden=hidden)
+    obs = np.load(GOLD / "flat_builder_7x7.npz")["obs"]
+    with Engine(concurrent_games=4, max_turns=120) as eng:
+        eng.load_weights(N.AR_ARCH_SYMMETRIC, 7, 7, sd)
+        out = eng.nn_forward(pods_array(specs))
+    if hidden == 128:
+        g = np.load(GOLD / "symmetric_7x7_h128.npz")
+        _check_vs_fp32(out, [g[k][idx] for k in ("policy_p1", "policy_p2", "value_p1", "value_p2")], 2.5e-2, 4e-2,
+                       "symmetric hidden 128 vs reference golden")
+    _check_vs_fp32(out, symmetric_forward(sd, obs[idx], 7, 7), 2.5e-2, 4e-2, f"symmetric hidden {hidden} fp32")
+
+
 def test_symmetric_swaps_outputs_when_players_swap():
     """Structural P1/P2 symmetry (symmetric.py:20-24): the two-rows-per-position mapping must keep it exactly."""
     specs, _ = _positions(7, 7, 96)
@@ -205,7 +225,7 @@ def test_cnn_and_symmetric_forward_other_boards(w, h, n):
 
 
 def test_unsupported_evaluator_shapes_fail_loudly():
-    sd = make_symmetric_state_dict(2, 7, 7, hidden=128)
+    sd = make_symmetric_state_dict(2, 7, 7, hidden=512)
     with Engine(concurrent_games=4, max_turns=120) as eng:
         with pytest.raises(RuntimeError, match="hidden_dim"):
             eng.load_weights(N.AR_ARCH_SYMMETRIC, 7, 7, sd)

@@ -94,6 +94,15 @@ def test_symmetric_and_cnn_restatements_match_reference_models(oracle, w, h):
             assert np.abs(a - g[k]).max() <= 1e-5, (name, k)
 
 
+def test_symmetric_restatement_matches_reference_model_hidden_128(oracle):
+    """SymmetricMLP(hidden_dim=128) of the real reference: the golden the zero-padded CUDA evaluator is held to."""
+    obs = _golden_obs(oracle, 7, 7)
+    out = symmetric_forward(make_symmetric_state_dict(4, 7, 7, hidden=128), obs, 7, 7)
+    g = np.load(GOLD / "symmetric_7x7_h128.npz")
+    for a, k in zip(out, ("policy_p1", "policy_p2", "value_p1", "value_p2")):
+        assert np.abs(a - g[k]).max() <= 1e-5, k
+
+
 def test_make_unmake_roundtrip(oracle):
     for spec in random_positions(40, 7, 7, seed=9):
         pod = pods_array([spec])
