@@ -628,7 +628,73 @@ struct Model : LeafEvaluator {
     }
   }
 
-  int load(const ar_tensor_desc* t, int n, int width, int height, std::string& err) override {
+  // A trunk narrower than the kernel's 64 channels runs zero-padded: every tensor with a channel axis is widened
+  // with zeros (BatchNorm: weight 0, bias 0, mean 0, variance 1 -> scale 0, shift 0), so the extra channels are exactly
+  // 0 in the stem, stay 0 through every pre-activation block (0 + 0 on the residual stream) and meet zero columns
+  // in pool_conv and in the combiner.  Same outputs as the narrow network; the 64-channel kernel is unchanged.
+  struct PaddedStateDict {
+    std::vector<std::vector<float>> store;
+    std::vector<ar_tensor_desc> descs;
+  };
+  static void pad_channels(const ar_tensor_desc* t, int n, int cr, PaddedStateDict& out) {
+    auto ends = [](const std::string& s, const char* suf) {
+      const size_t m = strlen(suf);
+      return s.size() >= m && s.compare(s.size() - m, m, suf) == 0;
+    };
+    for (int i = 0; i < n; ++i) {
+      const ar_tensor_desc& d = t[i];
+      const std::string name = d.name ? d.name : "";
+      bool pad0 = false, pad1 = false, comb = false;
+      float fill = 0.0f;
+      if (name == "stem.weight") pad0 = true;
+      else if (ends(name, ".conv1.weight") || ends(name, ".conv2.weight")) pad0 = pad1 = true;
+      else if (ends(name, ".pool_conv.weight")) pad1 = true;
+      else if (ends(name, ".pool_linear.weight") || ends(name, ".pool_linear.bias")) pad0 = true;
+      else if (name == "combiner.0.weight") comb = true;
+      else if (d.ndim == 1 && d.shape[0] == cr &&
+               (name.rfind("stem_bn.", 0) == 0 || name.find(".bn1.") != std::string::npos ||
+                name.find(".bn2.") != std::string::npos || name.find(".pool_bn.") != std::string::npos)) {
+        pad0 = true;
+        fill = ends(name, ".running_var") ? 1.0f : 0.0f;
+      }
+      if ((pad0 && d.shape[0] != cr) || (pad1 && (d.ndim < 2 || d.shape[1] != cr)) ||
+          (comb && (d.ndim != 2 || d.shape[1] <= cr))) {
+        pad0 = pad1 = comb = false;  // not the shape this trunk width implies: the loader reports it
+      }
+      if (!pad0 && !pad1 && !comb) { out.descs.push_back(d); continue; }
+      ar_tensor_desc nd = d;
+      const int64_t s0 = d.shape[0], s1 = d.ndim >= 2 ? d.shape[1] : 1;
+      int64_t inner = 1;
+      for (int k = 2; k < d.ndim; ++k) inner *= d.shape[k];
+      int64_t n0 = pad0 ? C : s0, n1 = pad1 ? C : s1;
+      if (comb) n1 = C + (s1 - cr);
+      out.store.emplace_back((size_t)(n0 * n1 * inner), fill);
+      float* dst = out.store.back().data();
+      for (int64_t a = 0; a < s0; ++a)
+        for (int64_t b = 0; b < s1; ++b) {
+          const int64_t nb = (comb && b >= cr) ? b - cr + C : b;
+          memcpy(dst + (a * n1 + nb) * inner, d.data + (a * s1 + b) * inner, (size_t)inner * sizeof(float));
+        }
+      nd.data = dst;
+      nd.shape[0] = n0;
+      if (d.ndim >= 2) nd.shape[1] = n1;
+      out.descs.push_back(nd);
+    }
+  }
+
+  int load(const ar_tensor_desc* t_in, int n_in, int width, int height, std::string& err) override {
+    const ar_tensor_desc* t = t_in;
+    int n = n_in;
+    PaddedStateDict padded;
+    {
+      const ar_tensor_desc* st0 = find_tensor(t, n, "stem.weight");
+      if (st0 && st0->ndim == 4 && st0->shape[0] >= 1 && st0->shape[0] < C) {
+        padded.store.reserve((size_t)n);  // the descriptors point into the vectors: no reallocation of the outer one
+        pad_channels(t, n, (int)st0->shape[0], padded);
+        t = padded.descs.data();
+        n = (int)padded.descs.size();
+      }
+    }
     const int S = width * height;
     if (find_tensor(t, n, "value_head.mlp.0.weight")) { err = "the `pooled` value head has no CUDA evaluator in this build"; return AR_ERR_UNSUPPORTED; }
     const ar_tensor_desc* st = find_tensor(t, n, "stem.weight");

@@ -204,6 +204,34 @@ def test_cnn_forward_matches_reference(tag, blocks, w, h, n):
                    f"cnn {tag} {w}x{h} n={n}")
 
 
+@pytest.mark.parametrize("channels,gpool", [(32, 16), (48, 32), (16, 16)])
+def test_cnn_narrower_trunks_run_zero_padded(channels, gpool):
+    """Trunks under 64 channels: the loader widens every channel axis with zeros (BatchNorm scale and shift 0), the
+    extra channels stay exactly 0 through the residual stream.  32 channels / gpool 16: against the real reference's
+    golden; the other widths against the fp32 restatement (validated against the reference at 32 and 64 channels)."""
+    n = 150
+    blocks = ("res", "gpool", "res")
+    specs, nb = _positions(7, 7, n)
+    idx = np.arange(n) % nb
+    sd = make_cnn_state_dict(6, blocks, channels=channels, gpool_channels=gpool)
+    obs = np.load(GOLD / "flat_builder_7x7.npz")["obs"]
+    with Engine(concurrent_games=4, max_turns=120) as eng:
+        eng.load_weights(N.AR_ARCH_CNN, 7, 7, sd)
+        out = eng.nn_forward(pods_array(specs))
+    if channels == 32:
+        g = np.load(GOLD / "cnn_gpool_7x7_c32.npz")
+        _check_vs_fp32(out, [g[k][idx] for k in ("policy_p1", "policy_p2", "value_p1", "value_p2")], 3e-2, 5e-2,
+                       "cnn 32 channels vs reference golden")
+    _check_vs_fp32(out, cnn_forward(sd, obs[idx], 7, 7), 3e-2, 5e-2, f"cnn {channels} channels fp32")
+
+
+def test_cnn_wider_than_64_channels_fails_loudly():
+    sd = make_cnn_state_dict(6, ("res",), channels=128)
+    with Engine(concurrent_games=4, max_turns=120) as eng:
+        with pytest.raises(RuntimeError, match="64"):
+            eng.load_weights(N.AR_ARCH_CNN, 7, 7, sd)
+
+
 @pytest.mark.parametrize("w,h,n", [(8, 8, 37), (6, 4, 100), (4, 4, 90), (4, 7, 61)])
 def test_cnn_and_symmetric_forward_other_boards(w, h, n):
     """Board geometries the golden files do not cover: one position per tile (8x8), non-square boards, five

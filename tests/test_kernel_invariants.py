@@ -70,3 +70,45 @@ def test_half_shared_memory_layout_fits_the_164_kb_carve_out():
     assert 32 * per_block <= 164 * 1024  # 32 one-warp blocks per SM
     # the move table is five wide: a cell has at most four open directions plus STAY
     assert 64 * 5 * 2 == 640 and 640 + 64 * 4 == 896
+
+
+def _pad_cnn_state_dict(sd: dict, cr: int, c: int = 64) -> dict:
+    """The widening rule of nn_cnn.cu `pad_channels`, restated: every channel axis grows to `c` with zeros
+    (BatchNorm running_var with ones), the combiner keeps its player columns after the 64 trunk columns."""
+    out = {}
+    for name, a in sd.items():
+        a = np.asarray(a)
+        if name == "stem.weight":
+            b = np.zeros((c,) + a.shape[1:], a.dtype); b[:cr] = a
+        elif name.endswith((".conv1.weight", ".conv2.weight")):
+            b = np.zeros((c, c) + a.shape[2:], a.dtype); b[:cr, :cr] = a
+        elif name.endswith(".pool_conv.weight"):
+            b = np.zeros((a.shape[0], c) + a.shape[2:], a.dtype); b[:, :cr] = a
+        elif name.endswith((".pool_linear.weight", ".pool_linear.bias")):
+            b = np.zeros((c,) + a.shape[1:], a.dtype); b[:cr] = a
+        elif name == "combiner.0.weight":
+            b = np.zeros((a.shape[0], c + a.shape[1] - cr), a.dtype); b[:, :cr] = a[:, :cr]; b[:, c:] = a[:, cr:]
+        elif a.ndim == 1 and a.shape[0] == cr and (name.startswith("stem_bn.") or ".bn1." in name or ".bn2." in name
+                                                     or ".pool_bn." in name):
+            b = np.full((c,), 1.0 if name.endswith(".running_var") else 0.0, a.dtype); b[:cr] = a
+        else:
+            b = a
+        out[name] = b
+    return out
+
+
+def test_zero_padded_cnn_trunk_is_the_same_network():
+    """The claim behind the CUDA loader's channel padding, checked with the fp32 restatement of PyRatCNN."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    from nn_ref import cnn_forward, make_cnn_state_dict
+
+    obs = np.load(Path(__file__).resolve().parent / "golden" / "flat_builder_7x7.npz")["obs"][:24]
+    for cr, g in ((32, 16), (16, 16), (48, 32)):
+        sd = make_cnn_state_dict(6, ("res", "gpool", "res"), channels=cr, gpool_channels=g)
+        a = cnn_forward(sd, obs, 7, 7)
+        b = cnn_forward(_pad_cnn_state_dict(sd, cr), obs, 7, 7)
+        for x, y in zip(a, b):
+            assert np.abs(x - y).max() <= 1e-6

@@ -103,6 +103,16 @@ def test_symmetric_restatement_matches_reference_model_hidden_128(oracle):
         assert np.abs(a - g[k]).max() <= 1e-5, k
 
 
+def test_cnn_restatement_matches_reference_model_32_channels(oracle):
+    """PyRatCNN with a 32-channel res / gpool16 / res trunk of the real reference: the golden the zero-padded CUDA
+    evaluator is held to."""
+    obs = _golden_obs(oracle, 7, 7)
+    out = cnn_forward(make_cnn_state_dict(6, ("res", "gpool", "res"), channels=32, gpool_channels=16), obs, 7, 7)
+    g = np.load(GOLD / "cnn_gpool_7x7_c32.npz")
+    for a, k in zip(out, ("policy_p1", "policy_p2", "value_p1", "value_p2")):
+        assert np.abs(a - g[k]).max() <= 1e-5, k
+
+
 def test_make_unmake_roundtrip(oracle):
     for spec in random_positions(40, 7, 7, seed=9):
         pod = pods_array([spec])
