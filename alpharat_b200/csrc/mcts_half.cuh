@@ -63,7 +63,7 @@ struct HalfCtx : WarpCtx {
   __device__ __forceinline__ void bind_half(uint8_t* base, NodeRec* pool_, int lane, uint32_t max_depth_, uint32_t batch_cap_) {
     bind(base, pool_, lane, max_depth_, batch_cap_);
     path = reinterpret_cast<uint32_t*>(sm + H_TP + (size_t)batch_cap_ * 8);
-    asm volatile("" : "+l"(path));
+    AR_OPAQUE(path);
     __builtin_assume(__isShared(path));
   }
 #ifdef AR_HALF_IDLE
