@@ -8,6 +8,12 @@
 // half executes the same sequence of collectives (same kind, same order) — a lane that arrives at a
 // different collective, or finishes early, aborts the run.
 //
+// Lanes run one after the other between two collectives, not in lockstep.  Code that is only correct because a warp
+// issues a load for all lanes before a later store of one lane (say, every lane reading a child-table word that lane 0
+// then overwrites, with no collective in between) therefore fails here although it works on the GPU: such a pattern is a
+// formal race under independent thread scheduling, and an experiment that introduced one was caught this way.
+// -DSIMT_BACKTRACE (with -O0 -g) prints the failing lane's return addresses and every lane's collective count.
+//
 // The product never includes this file (alpharat_b200/ has no reference to tests/).
 #pragma once
 #define AR_HOST_EMUL 1
@@ -22,6 +28,9 @@
 #endif
 
 #include <algorithm>
+#ifdef SIMT_BACKTRACE
+#include <execinfo.h>
+#endif
 
 // ---- CUDA keywords -------------------------------------------------------------------------------------
 #define __device__
@@ -133,6 +142,15 @@ static inline void switch_to(fiber_t* from, fiber_t* to) {
 
 static inline void fail(const char* what) {
   fprintf(stderr, "simt emulation: %s (lane %d)\n", what, g_half ? g_half->cur : -1);
+#ifdef SIMT_BACKTRACE  // g++ -O0 -g -DSIMT_BACKTRACE: return addresses of the failing lane for addr2line
+  void* bt[48];
+  const int n = backtrace(bt, 48);
+  backtrace_symbols_fd(bt, n, 2);
+  if (g_half)
+    for (int i = 0; i < LANES; ++i)
+      fprintf(stderr, "  lane %2d: collectives %llu, last kinds %u %u\n", i, (unsigned long long)g_half->seq[i],
+              g_half->kind[0][i], g_half->kind[1][i]);
+#endif
   abort();
 }
 
