@@ -59,98 +59,6 @@ struct RunParams {
   ar_progress* progress;  // mapped pinned host memory (may be null)
 };
 
-// Optional phase timers (-DAR_PHASE_TIMING): cycles per warp in gather / backup / advance.
-#ifdef AR_PHASE_TIMING
-#define AR_T0() long long _t0 = clock64()
-#define AR_T1(i) do { long long _t1 = clock64(); cx.phase[i] += (unsigned long long)(_t1 - _t0); _t0 = _t1; } while (0)
-#else
-#define AR_T0() do {} while (0)
-#define AR_T1(i) do {} while (0)
-#endif
-
-// One simulate_batch (search.rs:961-1073) with SmartUniformBackend fused in
-// (backend.rs:94-103: priors written when the node is created, values are 0).
-__device__ __forceinline__ void simulate_batch_uniform(WarpCtx& cx, const SearchParams& sp, Rng& rng,
-                                                       const GState& root_g, int root_turn,
-                                                       uint32_t bs, uint32_t& nn, uint32_t& term,
-                                                       uint32_t& coll, uint32_t coll_len, int lane) {
-  cx.epoch += 1;
-  cx.root_claimed = false;
-  AR_T0();
-  uint32_t ci = cx.node_count < coll_len ? cx.node_count : coll_len - 1;
-  int collisions_left = (int)cx.coll_table[ci];
-  int n_tp = 0;
-  while ((uint32_t)n_tp < bs && collisions_left > 0 && cx.error == 0) {
-    uint32_t budget = min((uint32_t)collisions_left, bs - (uint32_t)n_tp);
-    uint32_t c = pick_nodes<false>(cx, sp, rng, root_g, root_turn, budget, n_tp, true, lane);
-    collisions_left -= (int)c;
-    coll += c;
-  }
-  if (cx.error) return;
-  AR_T1(0);
-  for (int e = 0; e < n_tp; ++e) {
-    uint8_t kind = cx.tp()[e].kind;
-    if (kind == 1) term += 1; else nn += 1;
-    if (kind == 0 && cx.tp()[e].node == 0 && sp.noise_epsilon > 0.0f) apply_root_noise(cx, sp, rng, lane);
-    backup_entry<true>(cx, e, 0.0f, 0.0f, nullptr, nullptr, lane);
-  }
-  AR_T1(1);
-}
-
-__device__ __noinline__ void extract_and_store(WarpCtx& cx, const SearchParams& sp, int lane,
-                                               ar_search_result* out, uint32_t nn, uint32_t term,
-                                               uint32_t coll, float pol1[5], float pol2[5]) {
-  ar_search_result res;
-  extract_result(cx, sp, lane, res);
-  res.nn_evals = nn;
-  res.terminals = term;
-  res.collisions = coll;
-#pragma unroll
-  for (int a = 0; a < 5; ++a) { pol1[a] = res.policy_p1[a]; pol2[a] = res.policy_p2[a]; }
-  if (lane == 0) *out = res;
-}
-
-__device__ __forceinline__ void load_game(const ar_game_pod* pod, WarpCtx& cx, GState& g, int& turn,
-                                          int lane) {
-  cx.w = pod->width;
-  cx.cells = (int)pod->width * pod->height;
-  cx.max_turns = pod->max_turns;
-  turn = pod->turn;
-  __syncwarp();
-  for (int i = lane; i < 64; i += 32)  // 64 cells x 4 directions = 64 words
-    reinterpret_cast<uint32_t*>(cx.maze())[i] =
-        (i < cx.cells) ? reinterpret_cast<const uint32_t*>(pod->move_cost)[i] : 0u;
-  uint16_t* tbl = const_cast<uint16_t*>(cx.steptbl());
-  for (int i = lane; i < 64 * 8; i += 32) {  // move table by OUTCOME index: target cell | mud cost << 8
-    const int c = i >> 3, oi = i & 7;
-    uint32_t e = (uint32_t)c;  // STAY, and every slot past the cell's outcomes
-    if (c < cx.cells) {
-      // outcomes are the open directions in ascending action order, then STAY (compute_outcomes, node.rs:251-283)
-      int a = -1, seen = 0;
-#pragma unroll
-      for (int d = 0; d < 4; ++d)
-        if (pod->move_cost[c * 4 + d] != 0) {
-          if (seen == oi) a = d;
-          seen += 1;
-        }
-      if (a >= 0) {
-        const int cost = pod->move_cost[c * 4 + a];
-        const int mag = (a & 1) ? 1 : cx.w;
-        e = (uint32_t)(c + ((a & 2) ? -mag : mag)) | ((uint32_t)(cost >= 2 ? cost : 0) << 8);
-      }
-    }
-    tbl[i] = (uint16_t)e;
-  }
-  g.cheese = *reinterpret_cast<const uint64_t*>(pod->cheese);
-  g.p1 = pod->p1_y * pod->width + pod->p1_x;
-  g.p2 = pod->p2_y * pod->width + pod->p2_x;
-  g.mud1 = pod->p1_mud;
-  g.mud2 = pod->p2_mud;
-  g.s1x2 = __float2int_rn(pod->p1_score * 2.0f);
-  g.s2x2 = __float2int_rn(pod->p2_score * 2.0f);
-  __syncwarp();
-}
-
 // The uniform-prior self-play kernel: each warp claims games from an atomic counter
 // (game_worker_loop, selfplay.rs:609-650) and plays them to completion on device
 // (play_game, selfplay.rs:515-598).  search_only: one fresh-tree search per "game"

@@ -92,8 +92,8 @@ using std::min;
 // ---- the half: 16 fibers and their rendezvous -----------------------------------------------------------
 namespace simt {
 
-constexpr int LANES = 16;
-enum Kind : uint32_t { K_SHFL = 1, K_SHFL_XOR, K_SHFL_UP, K_SHFL_DOWN, K_BALLOT, K_SYNC };
+constexpr int MAX_LANES = 32;
+enum Kind : uint32_t { K_SHFL = 1, K_SHFL_XOR, K_SHFL_UP, K_SHFL_DOWN, K_BALLOT, K_SYNC, K_REDUCE, K_VOTE };
 
 // Fibre switch.  x86-64: save the callee-saved registers and swap stack pointers (swapcontext costs a system call per
 // switch — it saves the signal mask — and a search makes tens of thousands of them); elsewhere: ucontext.
@@ -115,16 +115,18 @@ typedef void* fiber_t;
 typedef ucontext_t fiber_t;
 #endif
 
-struct Half {
-  fiber_t ctx[LANES];
+struct Half {  // a group of lanes that executes collectives together: a half of a warp (16) or a whole warp (32)
+  fiber_t ctx[MAX_LANES];
   fiber_t main_ctx;
-  void* stacks[LANES] = {nullptr};
+  void* stacks[MAX_LANES] = {nullptr};
+  int step = 1;           // rotation order of the lanes: +1, or -1 (SIMT_REVERSE=1: a result that depends on it is a race)
+  int lanes = 16;         // 16: a half (mcts_half.cuh); 32: a warp (the one-tree-per-warp code of mcts_device.cuh)
   int cur = 0;            // lane that is running
-  int hbase = 0;          // 0 or 16: which half of the warp these lanes are
-  uint64_t seq[LANES] = {0};
-  uint32_t slot[2][LANES];
-  uint32_t kind[2][LANES];
-  bool done[LANES] = {false};
+  int hbase = 0;          // 0 or 16: which half of the warp these lanes are (0 for a whole warp)
+  uint64_t seq[MAX_LANES] = {0};
+  uint32_t slot[2][MAX_LANES];
+  uint32_t kind[2][MAX_LANES];
+  bool done[MAX_LANES] = {false};
   int n_done = 0;
   void (*body)(int lane, void* arg) = nullptr;
   void* arg = nullptr;
@@ -147,7 +149,7 @@ static inline void fail(const char* what) {
   const int n = backtrace(bt, 48);
   backtrace_symbols_fd(bt, n, 2);
   if (g_half)
-    for (int i = 0; i < LANES; ++i)
+    for (int i = 0; i < g_half->lanes; ++i)
       fprintf(stderr, "  lane %2d: collectives %llu, last kinds %u %u\n", i, (unsigned long long)g_half->seq[i],
               g_half->kind[0][i], g_half->kind[1][i]);
 #endif
@@ -163,7 +165,8 @@ static inline const uint32_t* rendezvous(uint32_t k, uint32_t v) {
   h.slot[par][me] = v;
   h.kind[par][me] = k;
   if (me == 0) h.collectives += 1;
-  const int next = (me + 1) % LANES;
+  const int LANES = h.lanes;
+  const int next = (me + h.step + LANES) % LANES;
   if (h.done[next]) fail("a lane finished while another is still executing collectives");
   h.cur = next;
   switch_to(&h.ctx[me], &h.ctx[next]);
@@ -177,6 +180,7 @@ static inline const uint32_t* rendezvous(uint32_t k, uint32_t v) {
 
 static void trampoline(int lane) {
   Half& h = *g_half;
+  const int LANES = h.lanes;
   h.body(lane, h.arg);
   h.done[lane] = true;
   h.n_done += 1;
@@ -188,7 +192,7 @@ static void trampoline(int lane) {
     h.cur = -1;
     switch_to(&dead, &h.main_ctx);
   }
-  const int next = (lane + 1) % LANES;
+  const int next = (lane + h.step + LANES) % LANES;
   h.cur = next;
   switch_to(&dead, &h.ctx[next]);
   abort();  // a finished lane is never resumed
@@ -197,10 +201,13 @@ static void trampoline(int lane) {
 static void fiber_entry() { trampoline(g_half->cur); }
 #endif
 
-// Run body(lane, arg) on the 16 lanes of a half (hbase 0 or 16) to completion.
-static inline uint64_t run_half(int hbase, void (*body)(int, void*), void* arg) {
+// Run body(lane, arg) on the 16 lanes of a half (hbase 0 or 16), or on the 32 lanes of a warp, to completion.
+static inline uint64_t run_half(int hbase, void (*body)(int, void*), void* arg, int lanes = 16) {
   static Half h;
   g_half = &h;
+  const int LANES = lanes;
+  h.lanes = lanes;
+  h.step = getenv("SIMT_REVERSE") ? -1 : 1;
   h.hbase = hbase;
   h.body = body;
   h.arg = arg;
@@ -227,8 +234,8 @@ static inline uint64_t run_half(int hbase, void (*body)(int, void*), void* arg) 
     makecontext(&h.ctx[i], (void (*)())trampoline, 1, i);
 #endif
   }
-  h.cur = 0;
-  switch_to(&h.main_ctx, &h.ctx[0]);
+  h.cur = h.step > 0 ? 0 : LANES - 1;
+  switch_to(&h.main_ctx, &h.ctx[h.cur]);
   return h.collectives;
 }
 
@@ -237,9 +244,10 @@ static inline int lane_in_half() { return g_half->cur; }
 }  // namespace simt
 
 // ---- warp collectives (member mask: the half that is executing, as in the kernel) -------------------------
-static inline unsigned __activemask() { return 0xffffu << simt::g_half->hbase; }
+static inline unsigned group_mask() { return simt::g_half->lanes == 32 ? 0xffffffffu : (0xffffu << simt::g_half->hbase); }
+static inline unsigned __activemask() { return group_mask(); }
 static inline void check_member_mask(unsigned mask) {
-  if (mask != (0xffffu << simt::g_half->hbase)) simt::fail("collective with a member mask that is not the executing half");
+  if (mask != group_mask()) simt::fail("collective with a member mask that is not the executing half / warp");
 }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) {
   check_member_mask(mask);
@@ -247,7 +255,7 @@ static inline void __syncwarp(unsigned mask = 0xffffffffu) {
 }
 static inline uint32_t __shfl_sync(unsigned mask, uint32_t v, int src, int width = 32) {
   check_member_mask(mask);
-  if (width > 16) simt::fail("full-warp shuffle in the half emulation");
+  if (width > simt::g_half->lanes) simt::fail("shuffle wider than the emulated group");
   const int me = simt::lane_in_half();
   const uint32_t* s = simt::rendezvous(simt::K_SHFL, v);
   return s[(me & ~(width - 1)) | (src & (width - 1))];
@@ -258,7 +266,7 @@ static inline float __shfl_sync(unsigned mask, float v, int src, int width = 32)
 }
 static inline uint32_t __shfl_xor_sync(unsigned mask, uint32_t v, int lanemask, int width = 32) {
   check_member_mask(mask);
-  if (width > 16) simt::fail("full-warp shuffle in the half emulation");
+  if (width > simt::g_half->lanes) simt::fail("shuffle wider than the emulated group");
   const int me = simt::lane_in_half();
   const uint32_t* s = simt::rendezvous(simt::K_SHFL_XOR, v);
   const int src = me ^ lanemask;
@@ -269,7 +277,7 @@ static inline float __shfl_xor_sync(unsigned mask, float v, int lanemask, int wi
 }
 static inline uint32_t __shfl_up_sync(unsigned mask, uint32_t v, unsigned delta, int width = 32) {
   check_member_mask(mask);
-  if (width > 16) simt::fail("full-warp shuffle in the half emulation");
+  if (width > simt::g_half->lanes) simt::fail("shuffle wider than the emulated group");
   const int me = simt::lane_in_half();
   const uint32_t* s = simt::rendezvous(simt::K_SHFL_UP, v);
   return ((me & (width - 1)) >= (int)delta) ? s[me - (int)delta] : s[me];
@@ -279,7 +287,7 @@ static inline float __shfl_up_sync(unsigned mask, float v, unsigned delta, int w
 }
 static inline uint32_t __shfl_down_sync(unsigned mask, uint32_t v, unsigned delta, int width = 32) {
   check_member_mask(mask);
-  if (width > 16) simt::fail("full-warp shuffle in the half emulation");
+  if (width > simt::g_half->lanes) simt::fail("shuffle wider than the emulated group");
   const int me = simt::lane_in_half();
   const uint32_t* s = simt::rendezvous(simt::K_SHFL_DOWN, v);
   return ((me & (width - 1)) + (int)delta < width) ? s[me + (int)delta] : s[me];
@@ -288,13 +296,31 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
   check_member_mask(mask);
   const uint32_t* s = simt::rendezvous(simt::K_BALLOT, pred ? 1u : 0u);
   unsigned b = 0;
-  for (int i = 0; i < simt::LANES; ++i) b |= (s[i] & 1u) << i;
+  for (int i = 0; i < simt::g_half->lanes; ++i) b |= (s[i] & 1u) << i;
   return b << simt::g_half->hbase;
 }
-// only the one-tree-per-warp code of mcts_device.cuh uses these; it is compiled but never run here
-static inline int __any_sync(unsigned, int) { simt::fail("__any_sync in the half emulation"); return 0; }
-static inline int __all_sync(unsigned, int) { simt::fail("__all_sync in the half emulation"); return 0; }
-static inline uint32_t __reduce_max_sync(unsigned, uint32_t) { simt::fail("__reduce_max_sync in the half emulation"); return 0; }
+// used by the one-tree-per-warp code of mcts_device.cuh (32-lane groups)
+static inline int __any_sync(unsigned mask, int pred) {
+  check_member_mask(mask);
+  const uint32_t* s = simt::rendezvous(simt::K_VOTE, pred ? 1u : 0u);
+  int r = 0;
+  for (int i = 0; i < simt::g_half->lanes; ++i) r |= (int)(s[i] & 1u);
+  return r;
+}
+static inline int __all_sync(unsigned mask, int pred) {
+  check_member_mask(mask);
+  const uint32_t* s = simt::rendezvous(simt::K_VOTE, pred ? 1u : 0u);
+  int r = 1;
+  for (int i = 0; i < simt::g_half->lanes; ++i) r &= (int)(s[i] & 1u);
+  return r;
+}
+static inline uint32_t __reduce_max_sync(unsigned mask, uint32_t v) {
+  check_member_mask(mask);
+  const uint32_t* s = simt::rendezvous(simt::K_REDUCE, v);
+  uint32_t m = 0;
+  for (int i = 0; i < simt::g_half->lanes; ++i) m = s[i] > m ? s[i] : m;
+  return m;
+}
 static inline uint32_t __reduce_min_sync(unsigned, uint32_t) { simt::fail("__reduce_min_sync in the half emulation"); return 0; }
 static inline uint32_t __reduce_add_sync(unsigned, uint32_t) { simt::fail("__reduce_add_sync in the half emulation"); return 0; }
 static inline uint32_t __reduce_or_sync(unsigned, uint32_t) { simt::fail("__reduce_or_sync in the half emulation"); return 0; }

@@ -1,4 +1,6 @@
-"""CPU parity of the two-trees-per-warp device code (alpharat_b200/csrc/mcts_half.cuh).
+"""CPU parity of the device code of the two warp-resident tree engines: two trees per warp
+(alpharat_b200/csrc/mcts_half.cuh, `emul` = "half") and one tree per warp (mcts_device.cuh, `emul` = "warp", 32 fibres
+running the per-warp loop of `selfplay_uniform_kernel`, tests/half_emul/warp_emul.cpp).
 
 The header is compiled for the host behind a shim of the CUDA intrinsics (tests/half_emul/simt_shim.h): the 16 lanes of
 a half run as 16 cooperative fibers, every shuffle / ballot / barrier is a rendezvous of the whole half, and the shim
@@ -18,13 +20,19 @@ import pytest
 from alpharat_b200.engine import search_cfg
 from alpharat_b200.games import GameSpec, make_games, pods_array
 from conftest import oracle_search, oracle_selfplay
-from half_emul_loader import emul_search, emul_selfplay, load_emul
+from half_emul_loader import emul_search, emul_selfplay, load_emul, load_warp_emul
 from test_gpu_parity_uniform import assert_result_equal, compare_selfplay
 
 
-@pytest.fixture(scope="module")
-def emul():
-    return load_emul()
+@pytest.fixture(scope="module", params=["half", "warp"])
+def emul(request):
+    e = load_emul() if request.param == "half" else load_warp_emul()
+    e.scale = 1.0 if request.param == "half" else 0.34  # 32 fibres per tree are slower: fewer games for the warp code
+    return e
+
+
+def _n(emul, n):
+    return max(2, int(n * emul.scale))
 
 
 def _check(emul, oracle, specs, cfg, seeds, pool_nodes=8192):
@@ -39,7 +47,7 @@ def _check(emul, oracle, specs, cfg, seeds, pool_nodes=8192):
 
 
 def test_config_a_5x5(emul, oracle):
-    n = 96
+    n = _n(emul, 96)
     _check(emul, oracle, make_games(n, width=5, height=5, cheese_count=5, max_turns=30),
            search_cfg(simulations=100, batch_size=8), list(range(n)))
 
@@ -47,14 +55,14 @@ def test_config_a_5x5(emul, oracle):
 def test_config_b_7x7_tuned(emul, oracle):
     """BASELINE config 2 parameters: tree reuse with in-place compaction, multi-visit levels once a tree holds 800
     nodes, parked split levels, forced playouts at the root."""
-    n = 12
+    n = _n(emul, 12)
     _check(emul, oracle, make_games(n, width=7, height=7, cheese_count=10, max_turns=50),
            search_cfg(simulations=1897, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103),
            [1000 + i for i in range(n)], pool_nodes=32768)
 
 
 def test_walls_mud_nonsquare(emul, oracle):
-    n = 32
+    n = _n(emul, 32)
     _check(emul, oracle, make_games(n, width=7, height=5, cheese_count=6, max_turns=40, maze_type="classic",
                                     positions="random", first_index=4000),
            search_cfg(simulations=300, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103),
@@ -62,7 +70,7 @@ def test_walls_mud_nonsquare(emul, oracle):
 
 
 def test_full_bitboard_8x8_large_batches_and_collision_budgets(emul, oracle):
-    n = 10
+    n = _n(emul, 10)
     _check(emul, oracle, make_games(n, width=8, height=8, cheese_count=20, max_turns=20, first_index=11),
            search_cfg(simulations=400, batch_size=64, c_puct=1.1, fpu_reduction=0.3, force_k=1.0,
                       collision_limit_min=4, collision_limit_max=64, collision_scaling_start=20,
@@ -73,10 +81,23 @@ def test_dirichlet_noise(emul, oracle):
     """Root noise on: the root's priors are no longer uniform, so its selections take the general path (prior shuffles,
     lane-chain sum of the visited mass) while every other node uses the tables; the Gamma sampler's f64 libm calls are
     the oracle's own on the host."""
-    n = 8
+    n = _n(emul, 8)
     _check(emul, oracle, make_games(n, width=7, height=7, cheese_count=10, max_turns=50, first_index=300),
            search_cfg(simulations=600, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103,
                       noise_epsilon=0.25, noise_concentration=10.83), [5000 + i for i in range(n)])
+
+
+def test_results_do_not_depend_on_the_order_in_which_the_lanes_run(emul, oracle, monkeypatch):
+    """The fibres of the shim run one after the other between two collectives; SIMT_REVERSE runs them in the opposite
+    order.  Code that needs a barrier it does not have (one lane stores, another reads) gives order-dependent results
+    here.  mcts_half.cuh passes as it is; the one-tree-per-warp code relies on the warp's lockstep in `save_path`, which
+    is marked there (AR_LOCKSTEP: a barrier in this host build only)."""
+    monkeypatch.setenv("SIMT_REVERSE", "1")
+    n = _n(emul, 12)
+    _check(emul, oracle, make_games(n, width=7, height=5, cheese_count=6, max_turns=40, maze_type="classic",
+                                    positions="random", first_index=4000),
+           search_cfg(simulations=300, batch_size=16, c_puct=0.512, fpu_reduction=0.459, force_k=0.103),
+           [31 * i + 5 for i in range(n)])
 
 
 def test_multi_visit_levels_and_tiny_searches(emul, oracle):
